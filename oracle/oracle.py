@@ -227,9 +227,15 @@ def contraction(alpha, p0, from0, size0, dim0, o0, conj0, v0, p1, from1, size1, 
         if l not in o0 and l not in o1:
             raise RuntimeError("o_r has unmatched dimensions")
     T = vr[0].dtype
-    # 1) vr <- beta*vr on the output range (dist.h:3145: copy(beta, vr -> vr))
-    vr_in = [x.copy() for x in vr]
-    copy(beta, pr, o_r, fromr, sizer, dimr, vr_in, pr, o_r, fromr, dimr, vr, co, Copy)
+    # 1) vr <- beta*vr on the output range (dist.h:3145: copy(beta, vr -> vr)).  Every part scales
+    #    its own elements; for partitions without overlaps that is exactly what the reference's
+    #    in-place copy does (with overlapping output parts the reference's in-place copy reads
+    #    already-scaled replicas, which is not a defined result, so tests use beta in {0,1} there).
+    pr_parts = np.asarray(pr, dtype=np.int64).reshape(len(vr), 2, len(o_r))
+    for j in range(len(vr)):
+        one = pr_parts[j:j + 1]
+        src = [vr[j].copy()]
+        copy(beta, one, o_r, fromr, sizer, dimr, src, one, o_r, fromr, dimr, [vr[j]], co, Copy)
     # 2) dense contraction of the two ranges in extended precision of the type
     W = np.complex128 if np.dtype(T).kind == "c" else np.float64
     X0 = _gather_global(p0, o0, from0, size0, dim0, v0, co).astype(W)

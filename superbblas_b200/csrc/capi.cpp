@@ -1,0 +1,305 @@
+// extern "C" entry points (include/superbblas_b200.h). Nothing here throws across the boundary.
+#include "contract_plan.hpp"
+#include "runtime.hpp"
+#include <cstring>
+#include <string>
+
+using namespace sbb;
+
+static thread_local std::string g_error;
+
+#define SBB_TRY(...)                                                                               \
+    try {                                                                                          \
+        __VA_ARGS__;                                                                               \
+        return 0;                                                                                  \
+    } catch (const std::exception &e) {                                                            \
+        g_error = e.what();                                                                        \
+        return 1;                                                                                  \
+    } catch (...) {                                                                                \
+        g_error = "unknown error";                                                                 \
+        return 1;                                                                                  \
+    }
+
+namespace {
+    Coor coor(const int *v, int n) { return v ? Coor(v, v + n) : Coor(n, 0); }
+
+    void store_boxes(const std::vector<Box> &b, int nd, int *out) {
+        for (size_t i = 0; i < b.size(); ++i) {
+            std::memcpy(out + (2 * i) * nd, b[i].from.data(), sizeof(int) * nd);
+            std::memcpy(out + (2 * i + 1) * nd, b[i].size.data(), sizeof(int) * nd);
+        }
+    }
+
+    std::string order_string(const char *o, int nd, const char *name) {
+        if ((o == nullptr && nd > 0) || (o != nullptr && (int)std::strlen(o) != nd))
+            throw std::runtime_error(
+                std::string("The length of the order should match the template argument; argument `") +
+                name + "` should have length " + std::to_string(nd));
+        return o ? std::string(o) : std::string();
+    }
+
+    CopyArgs make_copy_args(int nd0, const int *p0, int ncomp0, const char *o0, const int *from0,
+                            const int *size0, const int *dim0, int nd1, const int *p1, int ncomp1,
+                            const char *o1, const int *from1, const int *dim1, int nranks, int rank,
+                            int co, int copyadd) {
+        if (co != SBB_SLOW_TO_FAST && co != SBB_FAST_TO_SLOW)
+            throw std::runtime_error("invalid coordinate order");
+        if (copyadd != SBB_COPY && copyadd != SBB_ADD) throw std::runtime_error("invalid CopyAdd");
+        if (ncomp0 < 0 || ncomp1 < 0) throw std::runtime_error("wtf");
+        CopyArgs a;
+        a.nd0 = nd0, a.nd1 = nd1;
+        a.o0 = order_string(o0, nd0, "o0");
+        a.o1 = order_string(o1, nd1, "o1");
+        a.ncomp0 = ncomp0, a.ncomp1 = ncomp1;
+        a.nranks = nranks, a.rank = rank;
+        a.p0 = read_partition(p0, nranks * ncomp0, nd0);
+        a.p1 = read_partition(p1, nranks * ncomp1, nd1);
+        a.from0 = coor(from0, nd0), a.size0 = coor(size0, nd0), a.dim0 = coor(dim0, nd0);
+        a.from1 = coor(from1, nd1), a.dim1 = coor(dim1, nd1);
+        a.co = co;
+        a.add = copyadd == SBB_ADD;
+        return a;
+    }
+
+    std::vector<Buffer> buffers(const void *const *v, const sbb_context *ctx, int n) {
+        std::vector<Buffer> r(n);
+        for (int i = 0; i < n; ++i) {
+            r[i].ptr = v ? const_cast<void *>(v[i]) : nullptr;
+            if (ctx[i].plat == SBB_CPU)
+                r[i].host = true;
+            else if (ctx[i].plat == SBB_CUDA)
+                r[i].host = false, r[i].device = ctx[i].device;
+            else
+                throw std::runtime_error("Unsupported platform");
+        }
+        return r;
+    }
+
+    bool is_zero(int dtype, const double *a) {
+        const bool cplx = dtype == SBB_C64 || dtype == SBB_C128;
+        return a[0] == 0 && (!cplx || a[1] == 0);
+    }
+}
+
+extern "C" {
+
+const char *sbb_last_error(void) { return g_error.c_str(); }
+const char *sbb_version(void) { return "superbblas_b200 0.1 (sm_100a)"; }
+
+int sbb_device_count(int *count) {
+    SBB_TRY({
+        *count = 0;
+        cudaError_t e = cudaGetDeviceCount(count);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            *count = 0;
+        }
+    });
+}
+
+int sbb_sync(const sbb_context *ctx) {
+    SBB_TRY({
+        if (ctx->plat == SBB_CUDA) {
+            DeviceState &d = device_state(ctx->device);
+            use_device(ctx->device);
+            cuda_check(cudaStreamSynchronize(d.stream), "cudaStreamSynchronize");
+        }
+    });
+}
+
+int sbb_sync_legacy_stream(const sbb_context *ctx) {
+    SBB_TRY({
+        if (ctx->plat == SBB_CUDA) {
+            DeviceState &d = device_state(ctx->device);
+            use_device(ctx->device);
+            cuda_check(cudaEventRecord(d.ev_a, cudaStreamLegacy), "cudaEventRecord");
+            cuda_check(cudaStreamWaitEvent(d.stream, d.ev_a, 0), "cudaStreamWaitEvent");
+        }
+    });
+}
+
+int sbb_clear_caches(void) {
+    SBB_TRY({
+        clear_plan_cache();
+        pool_clear();
+    });
+}
+
+int sbb_clear_handles(void) { SBB_TRY(destroy_all_streams()); }
+
+int sbb_get_stream(int device, void **stream) { SBB_TRY(*stream = device_state(device).stream); }
+
+int sbb_launch_count(int reset, long long *count) { SBB_TRY(*count = launch_count(reset != 0)); }
+
+int sbb_comm_unique_id(void *id128) { SBB_TRY(nccl_unique_id(id128)); }
+
+int sbb_comm_create(const void *id128, int nranks, int rank, int device, sbb_comm_t *comm) {
+    SBB_TRY(*comm = (sbb_comm_t)comm_create(id128, nranks, rank, device));
+}
+
+int sbb_comm_destroy(sbb_comm_t comm) { SBB_TRY(comm_destroy((Comm *)comm)); }
+
+int sbb_comm_rank(sbb_comm_t comm, int *rank, int *nranks) {
+    SBB_TRY({
+        Comm *c = (Comm *)comm;
+        *rank = c ? c->rank : 0;
+        *nranks = c ? c->nranks : 1;
+    });
+}
+
+int sbb_partitioning_distributed_procs(int nd, const char *order, const int *dim,
+                                       const char *dist_labels, int nprocs, int *out) {
+    SBB_TRY({
+        Coor r = partitioning_distributed_procs(order_string(order, nd, "order"), coor(dim, nd),
+                                                dist_labels ? dist_labels : "", (unsigned)nprocs);
+        std::memcpy(out, r.data(), sizeof(int) * nd);
+    });
+}
+
+int sbb_basic_partitioning(int nd, const char *order, const int *dim, const int *procs,
+                           const char *dist_labels, int nprocs, int ncomponents, int *out) {
+    SBB_TRY(store_boxes(
+        basic_partitioning(order, coor(dim, nd), coor(procs, nd), dist_labels, nprocs, ncomponents),
+        nd, out));
+}
+
+int sbb_basic_partitioning_ext(int nd, const int *dim, const int *procs, int nprocs, int replicate,
+                               const int *ext_power, int *out) {
+    SBB_TRY(store_boxes(basic_partitioning_ext(coor(dim, nd), coor(procs, nd), nprocs,
+                                               replicate != 0, coor(ext_power, nd)),
+                        nd, out));
+}
+
+int sbb_make_hole(int nd, const int *from, const int *size, const int *hole_from,
+                  const int *hole_size, const int *dim, int *out, int max_out, int *nout) {
+    SBB_TRY({
+        auto r = make_hole(coor(from, nd), coor(size, nd), coor(hole_from, nd), coor(hole_size, nd),
+                           coor(dim, nd));
+        if ((int)r.size() > max_out) throw std::runtime_error("make_hole: output buffer too small");
+        *nout = (int)r.size();
+        store_boxes(r, nd, out);
+    });
+}
+
+int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0, int ncomponents0,
+             const char *o0, const int *from0, const int *size0, const int *dim0,
+             const void *const *v0, const float *const *mask0, const sbb_context *ctx0, int nd1,
+             const int *p1, int ncomponents1, const char *o1, const int *from1, const int *dim1,
+             void *const *v1, const float *const *mask1, const sbb_context *ctx1, sbb_comm_t comm,
+             int co, int copyadd) {
+    SBB_TRY({
+        Comm *c = (Comm *)comm;
+        for (int i = 0; mask0 && i < ncomponents0; ++i)
+            if (mask0[i]) throw std::runtime_error("copy: masks are not implemented");
+        for (int i = 0; mask1 && i < ncomponents1; ++i)
+            if (mask1[i]) throw std::runtime_error("copy: masks are not implemented");
+        CopyArgs a = make_copy_args(nd0, p0, ncomponents0, o0, from0, size0, dim0, nd1, p1,
+                                    ncomponents1, o1, from1, dim1, c ? c->nranks : 1,
+                                    c ? c->rank : 0, co, copyadd);
+        dtype_bytes(dtype0);
+        a.alpha_is_zero = is_zero(dtype0, alpha);
+        a.wire_align = 16 / dtype_bytes((a.add && dtype0 != dtype1) ? dtype0 : dtype1);
+        auto plan = get_copy_plan(a);
+        execute_copy(*plan, a, dtype0, dtype1, alpha, buffers(v0, ctx0, ncomponents0),
+                     buffers((const void *const *)v1, ctx1, ncomponents1), c);
+    });
+}
+
+int sbb_copy_plan_describe(int elem_size1, int nd0, const int *p0, int ncomponents0, const char *o0,
+                           const int *from0, const int *size0, const int *dim0, int nd1,
+                           const int *p1, int ncomponents1, const char *o1, const int *from1,
+                           const int *dim1, int nranks, int rank, int co, int copyadd,
+                           int alpha_is_zero, char *buf, size_t buflen, size_t *needed) {
+    try {
+        CopyArgs a = make_copy_args(nd0, p0, ncomponents0, o0, from0, size0, dim0, nd1, p1,
+                                    ncomponents1, o1, from1, dim1, nranks, rank, co, copyadd);
+        a.alpha_is_zero = alpha_is_zero != 0;
+        a.wire_align = elem_size1 > 0 && elem_size1 <= 16 ? 16 / elem_size1 : 1;
+        const std::string s = make_copy_plan(a)->describe();
+        if (needed) *needed = s.size() + 1;
+        if (s.size() + 1 > buflen) {
+            g_error = "buffer too small";
+            return 2;
+        }
+        std::memcpy(buf, s.c_str(), s.size() + 1);
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return 1;
+    }
+}
+
+int sbb_contraction(int dtype, const double *alpha, int nd0, const int *p0, const int *from0,
+                    const int *size0, const int *dim0, int ncomponents0, const char *o0, int conj0,
+                    const void *const *v0, const sbb_context *ctx0, int nd1, const int *p1,
+                    const int *from1, const int *size1, const int *dim1, int ncomponents1,
+                    const char *o1, int conj1, const void *const *v1, const sbb_context *ctx1,
+                    const double *beta, int ndo, const int *pr, const int *fromr, const int *sizer,
+                    const int *dimr, int ncomponentsr, const char *o_r, void *const *vr,
+                    const sbb_context *ctxr, sbb_comm_t comm, int co) {
+    SBB_TRY({
+        Comm *c = (Comm *)comm;
+        const int nranks = c ? c->nranks : 1, rank = c ? c->rank : 0;
+        if (co != SBB_SLOW_TO_FAST && co != SBB_FAST_TO_SLOW)
+            throw std::runtime_error("invalid coordinate order");
+        ContractionArgs a;
+        a.dtype = dtype;
+        a.alpha[0] = alpha[0], a.alpha[1] = alpha[1];
+        a.beta[0] = beta[0], a.beta[1] = beta[1];
+        a.co = co, a.nranks = nranks, a.rank = rank;
+        auto fill = [&](TensorArg &t, int nd, const int *p, const int *from, const int *size,
+                        const int *dim, int ncomp, const char *o, const char *name) {
+            t.nd = nd;
+            t.o = order_string(o, nd, name);
+            t.ncomp = ncomp;
+            t.p = read_partition(p, nranks * ncomp, nd);
+            t.from = coor(from, nd), t.size = coor(size, nd), t.dim = coor(dim, nd);
+        };
+        fill(a.t0, nd0, p0, from0, size0, dim0, ncomponents0, o0, "o0");
+        fill(a.t1, nd1, p1, from1, size1, dim1, ncomponents1, o1, "o1");
+        fill(a.tr, ndo, pr, fromr, sizer, dimr, ncomponentsr, o_r, "o_r");
+        a.conj0 = conj0 != 0, a.conj1 = conj1 != 0;
+        execute_contraction(a, buffers(v0, ctx0, ncomponents0), buffers(v1, ctx1, ncomponents1),
+                            buffers((const void *const *)vr, ctxr, ncomponentsr), c);
+    });
+}
+
+int sbk_permute_copy(const sbk_box_desc *box, const void *src, int dtype_src, void *dst,
+                     int dtype_dst, const double *alpha, int add, int device, void *stream) {
+    SBB_TRY({
+        DeviceState &d = device_state(device);
+        use_device(device);
+        permute_copy(*box, src, dtype_src, dst, dtype_dst, alpha, add != 0, device,
+                     stream ? (cudaStream_t)stream : d.stream);
+    });
+}
+
+int sbk_permute_describe(const sbk_box_desc *box, int dtype_src, int dtype_dst, const double *alpha,
+                         int add, const void *src, const void *dst, char *buf, size_t buflen) {
+    SBB_TRY({
+        std::string s;
+        permute_copy(*box, src, dtype_src, const_cast<void *>(dst), dtype_dst, alpha, add != 0, 0,
+                     nullptr, &s);
+        std::snprintf(buf, buflen, "%s", s.c_str());
+    });
+}
+
+int sbk_contract(const sbk_contract_desc *desc, int dtype, const double *alpha, const void *v0,
+                 const void *v1, const double *beta, void *vr, int device, void *stream) {
+    SBB_TRY({
+        DeviceState &d = device_state(device);
+        use_device(device);
+        contract(*desc, dtype, alpha, v0, v1, beta, vr, device,
+                 stream ? (cudaStream_t)stream : d.stream);
+    });
+}
+
+int sbk_contract_describe(const sbk_contract_desc *desc, int dtype, char *buf, size_t buflen) {
+    SBB_TRY({
+        std::string s;
+        const double one[2] = {1, 0};
+        contract(*desc, dtype, one, nullptr, nullptr, one, nullptr, 0, nullptr, &s);
+        std::snprintf(buf, buflen, "%s", s.c_str());
+    });
+}
+}

@@ -1,0 +1,32 @@
+// Internal interface between the host runtime and the CUDA kernels.
+#pragma once
+#include "../../include/superbblas_b200.h"
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+
+namespace sbb {
+
+    inline void cuda_check(cudaError_t e, const char *what) {
+        if (e != cudaSuccess)
+            throw std::runtime_error(std::string("CUDA error in ") + what + ": " +
+                                     cudaGetErrorString(e));
+    }
+
+    /// Count a kernel launch (reported by sbb_launch_count; bench.py's `gpu_launches`)
+    void count_launch();
+
+    int dtype_bytes(int dtype);
+
+    /// dst (+)= Q(alpha*src) over a strided box. The current device must be `device`.
+    /// If `describe` is given nothing is launched and the chosen variant is described instead.
+    void permute_copy(const sbk_box_desc &box, const void *src, int dtype_src, void *dst,
+                      int dtype_dst, const double *alpha, bool add, int device, cudaStream_t stream,
+                      std::string *describe = nullptr);
+
+    /// vr = alpha * sum_K f0(v0) f1(v1) + beta * vr. The current device must be `device`.
+    void contract(const sbk_contract_desc &desc, int dtype, const double *alpha, const void *v0,
+                  const void *v1, const double *beta, void *vr, int device, cudaStream_t stream,
+                  std::string *describe = nullptr);
+
+} // namespace sbb

@@ -1,0 +1,572 @@
+// Contraction kernels for sm_100a:  vr = alpha * sum_K f0(v0) * f1(v1) + beta * vr
+//
+// Replaces the reference's lowering "permute both operands -> xgemm_batch_strided -> add-copy"
+// (tensor.h:1271-1429 suggested_orders_for_contraction, tensor.h:1475-1598
+// local_contraction_normalized, blas.h:662-810 cublasGemmStridedBatchedEx).  Here the operands are
+// never re-laid-out: every label keeps its own stride (sbk_contract_desc) and the tile loaders
+// gather straight from the caller's layout, so the permutation is fused into the GEMM.
+//
+// Two kernels:
+//  * contract_mma_kernel (double, complex double): FP64 tensor-core path.  tcgen05 has no f64 kind,
+//    so on Blackwell FP64 matrix math is issued as warp-level DMMA (mma.sync.m8n8k4.f64).  A CTA
+//    owns a 64x64 output tile of one batch entry and one K-slice; operands flow
+//    global --cp.async (16 B per complex element, any stride)--> 4-stage shared-memory ring -->
+//    LDS.128 fragments --> DMMA, a complex product being four real DMMAs (the sign of the
+//    imaginary parts carries conj and the minus of i*i).  K is split across CTAs so that the grid
+//    fills 148 SMs x 2 CTAs for several waves even when the output is a single tile per batch
+//    entry (distillation shapes: M=N=64..128, K~1e5); partial tiles go to a workspace and
+//  * contract_reduce_kernel sums them in a fixed order (deterministic), applies alpha/beta/output
+//    strides (the reference's final add-copy, dist.h:3184, fused here).
+//  * contract_simt_kernel: any type, any shape; one thread per output element, K loop in registers,
+//    float types accumulate in double.  Used for small problems (e.g. site-wise colour-spin
+//    contractions with M=N=1) and for float / complex float.
+#include "kernels.hpp"
+#include "runtime.hpp"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <vector>
+
+namespace sbb {
+
+    namespace {
+
+        constexpr int GD = SBK_MAX_GROUP_DIMS;
+
+        struct Group {
+            int n;
+            int size[GD];
+            long long s0[GD], s1[GD], sr[GD];
+            long long vol;
+        };
+
+        struct ContractParams {
+            Group T, M, N, K;
+            int conj0, conj1;
+            // mma kernel
+            int mtiles, ntiles, ksplit, ksteps; // ksteps = ceil(K/BK)
+            int a_sr, a_sk, b_sr, b_sk;         // shared-memory strides (elements) of the operand tiles
+            int a_kfast, b_kfast;               // loader enumeration: 1 = k fastest, 0 = row fastest
+        };
+
+        __host__ __device__ inline long long group_offset(const Group &g, long long idx,
+                                                          const long long *stride) {
+            long long off = 0;
+#pragma unroll
+            for (int d = 0; d < GD; ++d)
+                if (d < g.n) {
+                    const long long c = idx % g.size[d];
+                    idx /= g.size[d];
+                    off += c * stride[d];
+                }
+            return off;
+        }
+
+        // ---- complex helpers ---------------------------------------------------------------------
+
+        template <typename T> struct Acc { using type = T; };
+        template <> struct Acc<float> { using type = double; };
+        template <> struct Acc<float2> { using type = double2; };
+
+        __device__ __forceinline__ double widen(float x) { return (double)x; }
+        __device__ __forceinline__ double widen(double x) { return x; }
+        __device__ __forceinline__ double2 widen(float2 x) { return make_double2(x.x, x.y); }
+        __device__ __forceinline__ double2 widen(double2 x) { return x; }
+        __device__ __forceinline__ double cj(double x) { return x; }
+        __device__ __forceinline__ double2 cj(double2 x) { return make_double2(x.x, -x.y); }
+        __device__ __forceinline__ void fma_acc(double &acc, double a, double b) { acc = fma(a, b, acc); }
+        __device__ __forceinline__ void fma_acc(double2 &acc, double2 a, double2 b) {
+            acc.x = fma(a.x, b.x, acc.x);
+            acc.x = fma(-a.y, b.y, acc.x);
+            acc.y = fma(a.x, b.y, acc.y);
+            acc.y = fma(a.y, b.x, acc.y);
+        }
+        __device__ __forceinline__ double mulc(double a, double b) { return a * b; }
+        __device__ __forceinline__ double2 mulc(double2 a, double2 b) {
+            return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+        }
+        __device__ __forceinline__ double addc(double a, double b) { return a + b; }
+        __device__ __forceinline__ double2 addc(double2 a, double2 b) {
+            return make_double2(a.x + b.x, a.y + b.y);
+        }
+        template <typename T> __device__ __forceinline__ T narrow(typename Acc<T>::type x);
+        template <> __device__ __forceinline__ float narrow<float>(double x) { return (float)x; }
+        template <> __device__ __forceinline__ double narrow<double>(double x) { return x; }
+        template <> __device__ __forceinline__ float2 narrow<float2>(double2 x) {
+            return make_float2((float)x.x, (float)x.y);
+        }
+        template <> __device__ __forceinline__ double2 narrow<double2>(double2 x) { return x; }
+        template <typename A> __device__ __forceinline__ A zero_acc();
+        template <> __device__ __forceinline__ double zero_acc<double>() { return 0.0; }
+        template <> __device__ __forceinline__ double2 zero_acc<double2>() {
+            return make_double2(0.0, 0.0);
+        }
+        template <typename A> __device__ __forceinline__ bool is_zero_acc(A x);
+        template <> __device__ __forceinline__ bool is_zero_acc<double>(double x) { return x == 0; }
+        template <> __device__ __forceinline__ bool is_zero_acc<double2>(double2 x) {
+            return x.x == 0 && x.y == 0;
+        }
+
+        // ---- generic kernel ------------------------------------------------------------------------
+
+        template <typename T>
+        __global__ void __launch_bounds__(256)
+            contract_simt_kernel(const __grid_constant__ ContractParams p, const T *__restrict__ v0,
+                                 const T *__restrict__ v1, T *vr, typename Acc<T>::type alpha,
+                                 typename Acc<T>::type beta) {
+            using A = typename Acc<T>::type;
+            const long long total = p.T.vol * p.M.vol * p.N.vol;
+            for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+                 idx += (long long)gridDim.x * blockDim.x) {
+                // output enumeration: n fastest, then m, then t
+                const long long n = idx % p.N.vol, m = (idx / p.N.vol) % p.M.vol,
+                                t = idx / (p.N.vol * p.M.vol);
+                const long long o0 = group_offset(p.T, t, p.T.s0) + group_offset(p.M, m, p.M.s0);
+                const long long o1 = group_offset(p.T, t, p.T.s1) + group_offset(p.N, n, p.N.s1);
+                const long long orr = group_offset(p.T, t, p.T.sr) + group_offset(p.M, m, p.M.sr) +
+                                      group_offset(p.N, n, p.N.sr);
+                A acc = zero_acc<A>();
+                if (p.K.n <= 1) {
+                    const long long k0 = p.K.n ? p.K.s0[0] : 0, k1 = p.K.n ? p.K.s1[0] : 0;
+                    for (long long k = 0; k < p.K.vol; ++k) {
+                        A a = widen(v0[o0 + k * k0]), b = widen(v1[o1 + k * k1]);
+                        if (p.conj0) a = cj(a);
+                        if (p.conj1) b = cj(b);
+                        fma_acc(acc, a, b);
+                    }
+                } else {
+                    for (long long k = 0; k < p.K.vol; ++k) {
+                        A a = widen(v0[o0 + group_offset(p.K, k, p.K.s0)]),
+                          b = widen(v1[o1 + group_offset(p.K, k, p.K.s1)]);
+                        if (p.conj0) a = cj(a);
+                        if (p.conj1) b = cj(b);
+                        fma_acc(acc, a, b);
+                    }
+                }
+                A r = mulc(alpha, acc);
+                if (!is_zero_acc(beta)) r = addc(r, mulc(beta, widen(vr[orr])));
+                vr[orr] = narrow<T>(r);
+            }
+        }
+
+        // ---- FP64 tensor-core kernel -----------------------------------------------------------------
+
+        constexpr int BM = 64, BN = 64, BK = 8, STAGES = 4, MMA_THREADS = 128;
+
+        __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(d0), "+d"(d1)
+                         : "d"(a), "d"(b));
+        }
+
+        template <int BYTES>
+        __device__ __forceinline__ void cp_async(void *smem, const void *gmem, bool valid) {
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem);
+            const int src = valid ? BYTES : 0; // src-size 0: the destination is zero filled
+            asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(saddr), "l"(gmem),
+                         "n"(BYTES), "r"(src));
+        }
+        __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+        template <int N> __device__ __forceinline__ void cp_async_wait() {
+            asm volatile("cp.async.wait_group %0;" ::"n"(N));
+        }
+
+        template <typename T> struct Frag; // fragment element as loaded from shared memory
+        template <> struct Frag<double> {
+            static constexpr bool cplx = false;
+        };
+        template <> struct Frag<double2> {
+            static constexpr bool cplx = true;
+        };
+
+        /// Offset of contracted index k in an operand
+        __device__ __forceinline__ long long k_offset(const Group &K, long long k,
+                                                      const long long *stride) {
+            if (K.n == 1) return k * stride[0];
+            return group_offset(K, k, stride);
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(MMA_THREADS, 2)
+            contract_mma_kernel(const __grid_constant__ ContractParams p, const T *__restrict__ v0,
+                                const T *__restrict__ v1, T *__restrict__ ws) {
+            constexpr bool CPLX = Frag<T>::cplx;
+            constexpr int ACC = CPLX ? 4 : 2; // doubles per 8x8 block per lane
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            // stage layout: [A tile | B tile], sizes fixed by the host (a_stage, b_stage elements)
+            const int a_stage = p.a_kfast ? BM * p.a_sr : BK * p.a_sk;
+            const int b_stage = p.b_kfast ? BN * p.b_sr : BK * p.b_sk;
+            T *smem = reinterpret_cast<T *>(smem_raw);
+            const int stage_elems = a_stage + b_stage;
+
+            const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+            const int wm = warp >> 1, wn = warp & 1; // 2x2 warps, 32x32 each
+
+            // ---- which tile / K slice ------------------------------------------------------------
+            long long bid = blockIdx.x;
+            const int nt = (int)(bid % p.ntiles);
+            bid /= p.ntiles;
+            const int mt = (int)(bid % p.mtiles);
+            bid /= p.mtiles;
+            const int ks = (int)(bid % p.ksplit);
+            const long long t = bid / p.ksplit;
+            const int kstep0 = (int)((long long)p.ksteps * ks / p.ksplit);
+            const int kstep1 = (int)((long long)p.ksteps * (ks + 1) / p.ksplit);
+            const int nsteps = kstep1 - kstep0;
+
+            const T *a_base = v0 + group_offset(p.T, t, p.T.s0);
+            const T *b_base = v1 + group_offset(p.T, t, p.T.s1);
+
+            // ---- loader slots: 4 elements of A and 4 of B per thread and stage ----------------------
+            constexpr int A_SLOTS = BM * BK / MMA_THREADS, B_SLOTS = BN * BK / MMA_THREADS;
+            long long a_row[A_SLOTS], b_row[B_SLOTS];
+            int a_kk[A_SLOTS], b_kk[B_SLOTS], a_sm[A_SLOTS], b_sm[B_SLOTS];
+#pragma unroll
+            for (int i = 0; i < A_SLOTS; ++i) {
+                const int slot = tid + i * MMA_THREADS;
+                const int r = p.a_kfast ? slot / BK : slot % BM, kk = p.a_kfast ? slot % BK : slot / BM;
+                const long long m = min((long long)mt * BM + r, p.M.vol - 1); // clamp: rows past M are never read back
+                a_row[i] = group_offset(p.M, m, p.M.s0);
+                a_kk[i] = kk;
+                a_sm[i] = r * p.a_sr + kk * p.a_sk;
+            }
+#pragma unroll
+            for (int i = 0; i < B_SLOTS; ++i) {
+                const int slot = tid + i * MMA_THREADS;
+                const int r = p.b_kfast ? slot / BK : slot % BN, kk = p.b_kfast ? slot % BK : slot / BN;
+                const long long n = min((long long)nt * BN + r, p.N.vol - 1);
+                b_row[i] = group_offset(p.N, n, p.N.s1);
+                b_kk[i] = kk;
+                b_sm[i] = a_stage + r * p.b_sr + kk * p.b_sk;
+            }
+
+            auto load_stage = [&](int stage, int kstep) {
+                T *s = smem + (size_t)stage * stage_elems;
+                const long long kbase = (long long)kstep * BK;
+#pragma unroll
+                for (int i = 0; i < A_SLOTS; ++i) {
+                    const long long k = kbase + a_kk[i];
+                    const bool ok = k < p.K.vol;
+                    const long long off = ok ? a_row[i] + k_offset(p.K, k, p.K.s0) : 0;
+                    cp_async<sizeof(T)>(s + a_sm[i], a_base + off, ok);
+                }
+#pragma unroll
+                for (int i = 0; i < B_SLOTS; ++i) {
+                    const long long k = kbase + b_kk[i];
+                    const bool ok = k < p.K.vol;
+                    const long long off = ok ? b_row[i] + k_offset(p.K, k, p.K.s1) : 0;
+                    cp_async<sizeof(T)>(s + b_sm[i], b_base + off, ok);
+                }
+            };
+
+            // ---- accumulators: 4x4 blocks of 8x8 per warp ---------------------------------------------
+            double acc[4][4][ACC];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < ACC; ++c) acc[i][j][c] = 0.0;
+
+            // fragment addresses inside a stage: element (row = base + lane/4, k = lane%4)
+            int a_frag[4], b_frag[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a_frag[i] = (wm * 32 + i * 8 + (lane >> 2)) * p.a_sr + (lane & 3) * p.a_sk;
+                b_frag[i] = a_stage + (wn * 32 + i * 8 + (lane >> 2)) * p.b_sr + (lane & 3) * p.b_sk;
+            }
+            const double sa = p.conj0 ? -1.0 : 1.0, sb = p.conj1 ? -1.0 : 1.0;
+
+            // ---- pipeline -----------------------------------------------------------------------------
+#pragma unroll
+            for (int s = 0; s < STAGES - 1; ++s) {
+                if (s < nsteps) load_stage(s, kstep0 + s);
+                cp_async_commit();
+            }
+            for (int it = 0; it < nsteps; ++it) {
+                cp_async_wait<STAGES - 2>();
+                __syncthreads();
+                {
+                    const int nxt = it + STAGES - 1;
+                    if (nxt < nsteps) load_stage(nxt % STAGES, kstep0 + nxt);
+                    cp_async_commit();
+                }
+                const T *s = smem + (size_t)(it % STAGES) * stage_elems;
+#pragma unroll
+                for (int k4 = 0; k4 < BK / 4; ++k4) {
+                    if constexpr (CPLX) {
+                        double ar[4], ai[4], nai[4], br[4], bi[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const double2 a =
+                                *reinterpret_cast<const double2 *>(s + a_frag[i] + k4 * 4 * p.a_sk);
+                            const double2 b =
+                                *reinterpret_cast<const double2 *>(s + b_frag[i] + k4 * 4 * p.b_sk);
+                            ar[i] = a.x, ai[i] = sa * a.y, nai[i] = -ai[i];
+                            br[i] = b.x, bi[i] = sb * b.y;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                dmma(acc[i][j][0], acc[i][j][1], ar[i], br[j]);
+                                dmma(acc[i][j][0], acc[i][j][1], nai[i], bi[j]);
+                                dmma(acc[i][j][2], acc[i][j][3], ar[i], bi[j]);
+                                dmma(acc[i][j][2], acc[i][j][3], ai[i], br[j]);
+                            }
+                    } else {
+                        double a[4], b[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            a[i] = *reinterpret_cast<const double *>(s + a_frag[i] + k4 * 4 * p.a_sk);
+                            b[i] = *reinterpret_cast<const double *>(s + b_frag[i] + k4 * 4 * p.b_sk);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                    }
+                }
+            }
+            cp_async_wait<0>();
+
+            // ---- partial tile to the workspace: ws[((t*mt*nt tile) * ksplit + ks)][m][n] -------------
+            const long long tile_id = ((t * p.mtiles + mt) * p.ntiles + nt) * p.ksplit + ks;
+            T *out = ws + tile_id * (long long)(BM * BN);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int row = wm * 32 + i * 8 + (lane >> 2);
+                    const int col = wn * 32 + j * 8 + (lane & 3) * 2;
+                    if constexpr (CPLX) {
+                        double4 v0 = make_double4(acc[i][j][0], acc[i][j][2], acc[i][j][1],
+                                                  acc[i][j][3]);
+                        *reinterpret_cast<double4 *>(out + row * BN + col) = v0;
+                    } else {
+                        *reinterpret_cast<double2 *>(out + row * BN + col) =
+                            make_double2(acc[i][j][0], acc[i][j][1]);
+                    }
+                }
+        }
+
+        /// Sum the K-slices of every output tile in a fixed order and write alpha*sum + beta*vr
+        template <typename T>
+        __global__ void __launch_bounds__(256)
+            contract_reduce_kernel(const __grid_constant__ ContractParams p, const T *__restrict__ ws,
+                                   T *vr, T alpha, T beta) {
+            const long long total = p.T.vol * p.M.vol * p.N.vol;
+            for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+                 idx += (long long)gridDim.x * blockDim.x) {
+                const long long n = idx % p.N.vol, m = (idx / p.N.vol) % p.M.vol,
+                                t = idx / (p.N.vol * p.M.vol);
+                const int mt = (int)(m / BM), nt = (int)(n / BN);
+                const long long tile0 = ((t * p.mtiles + mt) * p.ntiles + nt) * p.ksplit;
+                const T *src = ws + tile0 * (long long)(BM * BN) + (m % BM) * BN + (n % BN);
+                T acc = src[0];
+                for (int s = 1; s < p.ksplit; ++s) acc = addc(acc, src[(long long)s * BM * BN]);
+                const long long orr = group_offset(p.T, t, p.T.sr) + group_offset(p.M, m, p.M.sr) +
+                                      group_offset(p.N, n, p.N.sr);
+                T r = mulc(alpha, acc);
+                if (!is_zero_acc(beta)) r = addc(r, mulc(beta, vr[orr]));
+                vr[orr] = r;
+            }
+        }
+
+        // ---- host ----------------------------------------------------------------------------------
+
+        /// Copy one label group, dropping extent-1 labels and merging neighbours that stay affine in
+        /// every tensor; dims are sorted by the stride in `key` (0: s0, 1: s1, 2: sr)
+        Group make_group(const sbk_contract_dim *d, int n, int key) {
+            std::vector<sbk_contract_dim> v;
+            for (int i = 0; i < n; ++i) {
+                if (d[i].size <= 0) {
+                    Group g;
+                    std::memset(&g, 0, sizeof g);
+                    g.vol = 0;
+                    return g;
+                }
+                if (d[i].size > 1) v.push_back(d[i]);
+            }
+            auto keyof = [&](const sbk_contract_dim &x) { return key == 0 ? x.s0 : key == 1 ? x.s1 : x.sr; };
+            std::stable_sort(v.begin(), v.end(), [&](const sbk_contract_dim &a, const sbk_contract_dim &b) {
+                return keyof(a) < keyof(b);
+            });
+            std::vector<sbk_contract_dim> m;
+            for (const auto &x : v) {
+                if (!m.empty()) {
+                    auto &l = m.back();
+                    const long long s = l.size;
+                    if (l.s0 * s == x.s0 && l.s1 * s == x.s1 && l.sr * s == x.sr &&
+                        s * (long long)x.size < (1ll << 31)) {
+                        l.size *= x.size;
+                        continue;
+                    }
+                }
+                m.push_back(x);
+            }
+            if ((int)m.size() > GD) throw std::runtime_error("contraction: too many labels in a group");
+            Group g;
+            std::memset(&g, 0, sizeof g);
+            g.n = (int)m.size();
+            g.vol = 1;
+            for (int i = 0; i < g.n; ++i) {
+                g.size[i] = m[i].size, g.s0[i] = m[i].s0, g.s1[i] = m[i].s1, g.sr[i] = m[i].sr;
+                g.vol *= m[i].size;
+            }
+            return g;
+        }
+
+        int sm_count(int device) {
+            static int sms[64] = {0};
+            if (!sms[device])
+                cuda_check(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device),
+                           "cudaDeviceGetAttribute");
+            return sms[device];
+        }
+
+        template <typename T> T scalar_of(const double *a);
+        template <> double scalar_of<double>(const double *a) { return a[0]; }
+        template <> double2 scalar_of<double2>(const double *a) { return make_double2(a[0], a[1]); }
+
+        template <typename T>
+        void launch_simt(const ContractParams &p, const double *alpha, const void *v0, const void *v1,
+                         const double *beta, void *vr, int device, cudaStream_t stream) {
+            using A = typename Acc<T>::type;
+            const long long total = p.T.vol * p.M.vol * p.N.vol;
+            const unsigned grid =
+                (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(device) * 16);
+            contract_simt_kernel<T><<<grid, 256, 0, stream>>>(p, (const T *)v0, (const T *)v1, (T *)vr,
+                                                             scalar_of<A>(alpha), scalar_of<A>(beta));
+            count_launch();
+            cuda_check(cudaGetLastError(), "contract_simt_kernel launch");
+        }
+
+        /// Shared-memory layout of an operand tile: k-contiguous operands are stored [row][k] with
+        /// row stride = BK + pad, row-contiguous operands [k][row]; the pads make the fragment
+        /// LDS conflict free (see the derivation in DESIGN.md).
+        void tile_layout(bool kfast, int esize, int rows, int &sr, int &sk) {
+            if (kfast) {
+                sr = BK + 4; // 12: = 4 mod 8 (16 B elements) and in {4,12} mod 16 (8 B elements)
+                sk = 1;
+            } else {
+                sk = rows + (esize == 16 ? 2 : 4);
+                sr = 1;
+            }
+        }
+
+        template <typename T>
+        void launch_mma(ContractParams p, const double *alpha, const void *v0, const void *v1,
+                        const double *beta, void *vr, int device, cudaStream_t stream,
+                        std::string *describe) {
+            p.mtiles = (int)((p.M.vol + BM - 1) / BM);
+            p.ntiles = (int)((p.N.vol + BN - 1) / BN);
+            p.ksteps = (int)((p.K.vol + BK - 1) / BK);
+            // operand enumeration: follow the contiguous direction in global memory
+            p.a_kfast = p.K.n > 0 && (p.M.n == 0 || p.K.s0[0] <= p.M.s0[0]);
+            p.b_kfast = p.K.n > 0 && (p.N.n == 0 || p.K.s1[0] <= p.N.s1[0]);
+            tile_layout(p.a_kfast, sizeof(T), BM, p.a_sr, p.a_sk);
+            tile_layout(p.b_kfast, sizeof(T), BN, p.b_sr, p.b_sk);
+            const int a_stage = p.a_kfast ? BM * p.a_sr : BK * p.a_sk;
+            const int b_stage = p.b_kfast ? BN * p.b_sr : BK * p.b_sk;
+            const size_t smem = (size_t)(a_stage + b_stage) * STAGES * sizeof(T);
+
+            // K split: fill the machine for several waves, keep every slice long
+            const long long tiles = p.T.vol * p.mtiles * p.ntiles;
+            const long long slots = (long long)sm_count(device) * 2;
+            int best = 1;
+            double best_eff = -1;
+            const int smax = std::max(1, p.ksteps / 32);
+            for (int s = 1; s <= smax && s <= 1024; ++s) {
+                const long long ctas = tiles * s;
+                const long long waves = (ctas + slots - 1) / slots;
+                double eff = (double)ctas / (double)(waves * slots);
+                if (waves >= 6) eff += 1e-3; // prefer enough waves to hide the ragged tail
+                if (eff > best_eff + 1e-9) best_eff = eff, best = s;
+                if (waves >= 16) break;
+            }
+            p.ksplit = best;
+            const long long ctas = tiles * p.ksplit;
+            if (ctas >= (1ll << 31)) throw std::runtime_error("contraction: grid too large");
+            if (describe) {
+                std::stringstream ss;
+                ss << "mma f64 tile=" << BM << "x" << BN << "x" << BK << " stages=" << STAGES
+                   << " T=" << p.T.vol << " M=" << p.M.vol << " N=" << p.N.vol << " K=" << p.K.vol
+                   << " ksplit=" << p.ksplit << " ctas=" << ctas << " smem=" << smem
+                   << " a_kfast=" << p.a_kfast << " b_kfast=" << p.b_kfast;
+                *describe = ss.str();
+                return;
+            }
+            const size_t ws_bytes = (size_t)ctas * BM * BN * sizeof(T);
+            T *ws = (T *)pool_alloc(device, ws_bytes);
+            static bool attr_set[64] = {false};
+            if (!attr_set[device]) {
+                cuda_check(cudaFuncSetAttribute(contract_mma_kernel<T>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024),
+                           "cudaFuncSetAttribute");
+                attr_set[device] = true;
+            }
+            contract_mma_kernel<T><<<(unsigned)ctas, MMA_THREADS, smem, stream>>>(p, (const T *)v0,
+                                                                                 (const T *)v1, ws);
+            count_launch();
+            cuda_check(cudaGetLastError(), "contract_mma_kernel launch");
+            const long long total = p.T.vol * p.M.vol * p.N.vol;
+            const unsigned grid =
+                (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(device) * 8);
+            contract_reduce_kernel<T><<<grid, 256, 0, stream>>>(p, ws, (T *)vr, scalar_of<T>(alpha),
+                                                               scalar_of<T>(beta));
+            count_launch();
+            cuda_check(cudaGetLastError(), "contract_reduce_kernel launch");
+            pool_free(device, ws);
+        }
+
+    } // namespace
+
+    void contract(const sbk_contract_desc &desc, int dtype, const double *alpha, const void *v0,
+                  const void *v1, const double *beta, void *vr, int device, cudaStream_t stream,
+                  std::string *describe) {
+        if (dtype != SBB_F32 && dtype != SBB_F64 && dtype != SBB_C64 && dtype != SBB_C128)
+            throw std::runtime_error("contraction: unsupported type");
+        if (desc.nT > GD || desc.nM > GD || desc.nN > GD || desc.nK > GD || desc.nT < 0 ||
+            desc.nM < 0 || desc.nN < 0 || desc.nK < 0)
+            throw std::runtime_error("contraction: too many labels in a group");
+        ContractParams p;
+        std::memset(&p, 0, sizeof p);
+        p.T = make_group(desc.T, desc.nT, 2);
+        p.M = make_group(desc.M, desc.nM, 0);
+        p.N = make_group(desc.N, desc.nN, 1);
+        p.K = make_group(desc.K, desc.nK, 0);
+        p.conj0 = desc.conj0 != 0, p.conj1 = desc.conj1 != 0;
+        if (p.T.vol == 0 || p.M.vol == 0 || p.N.vol == 0) {
+            if (describe) *describe = "empty";
+            return;
+        }
+        // An empty contracted range leaves vr = beta*vr: the generic kernel handles K.vol == 0
+        const char *force = std::getenv("SBB_CONTRACT_KERNEL");
+        const bool f64 = dtype == SBB_F64 || dtype == SBB_C128;
+        bool use_mma = f64 && p.K.vol >= 64 && p.M.vol * p.N.vol >= 256 && p.M.vol >= 8 && p.N.vol >= 8;
+        if (force && std::strcmp(force, "simt") == 0) use_mma = false;
+        if (force && std::strcmp(force, "mma") == 0 && f64 && p.K.vol > 0) use_mma = true;
+        if (use_mma) {
+            if (dtype == SBB_F64)
+                launch_mma<double>(p, alpha, v0, v1, beta, vr, device, stream, describe);
+            else
+                launch_mma<double2>(p, alpha, v0, v1, beta, vr, device, stream, describe);
+            return;
+        }
+        if (describe) {
+            std::stringstream ss;
+            ss << "simt T=" << p.T.vol << " M=" << p.M.vol << " N=" << p.N.vol << " K=" << p.K.vol;
+            *describe = ss.str();
+            return;
+        }
+        switch (dtype) {
+        case SBB_F32: launch_simt<float>(p, alpha, v0, v1, beta, vr, device, stream); break;
+        case SBB_F64: launch_simt<double>(p, alpha, v0, v1, beta, vr, device, stream); break;
+        case SBB_C64: launch_simt<float2>(p, alpha, v0, v1, beta, vr, device, stream); break;
+        case SBB_C128: launch_simt<double2>(p, alpha, v0, v1, beta, vr, device, stream); break;
+        }
+    }
+
+} // namespace sbb

@@ -1,0 +1,884 @@
+// Permutation / reshuffle copy kernels for sm_100a.
+//
+// Replaces the reference's index-vector machinery: get_permutation (tensor.h:815-961, thrust K1),
+// copy_n / copy_n_blocking gather-scatter (copy_n.h:283-351, :752-987, thrust K2-K4) and zero_n
+// (copy_n.h:379).  No index vector exists here: a copy is a strided box (sbk_box_desc), and the
+// kernel walks it tile by tile.
+//
+// Kernel design (HBM-bound byte work; the rules that matter are coalescing, bytes in flight and
+// grid sizing, not tensor cores):
+//   * The box is canonicalised on the host: extent-1 dims dropped, dims sorted by destination
+//     stride, neighbouring dims merged when both sides stay affine, and the element widened to 8 or
+//     16 bytes when the fastest dim is shared and aligned (128-bit ld/st whenever possible).
+//   * A tile is a small sub-box chosen so that it holds a long contiguous run of the destination
+//     AND a long contiguous run of the source (>=256-512 B each when the geometry allows).
+//     CTAs are persistent (grid = SMs x resident CTAs) and stride over the tiles.
+//   * Inside a tile every thread owns up to EPT "slots".  The slot -> (source offset, shared-memory
+//     position) map for the load phase (threads consecutive along the SOURCE-contiguous direction)
+//     and the slot -> (destination offset, shared-memory position) map for the store phase
+//     (threads consecutive along the DESTINATION-contiguous direction) are tile invariant, so they
+//     are computed once per CTA and kept in registers: the per-element cost in the steady state
+//     is one load, one st.shared, one ld.shared, one store.  Tile coordinates advance with
+//     carry arithmetic (no division in the loop).
+//   * Shared memory is laid out in destination order; the stride of the source-fastest dim is
+//     padded to an odd number of elements so the transposing st.shared is bank-conflict free.
+//   * When source and destination enumerate the tile in the same order no staging is needed and
+//     the direct variant (no shared memory, no barrier) is used.
+//   * Typed variants apply alpha (without fused multiply-add, so results are bit-identical to the
+//     reference's CPU loops built with -ffp-contract=off), convert T->Q and add.
+#include "kernels.hpp"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <cuda_runtime.h>
+#include <map>
+#include <numeric>
+#include <sstream>
+#include <vector>
+
+namespace sbb {
+
+    namespace {
+
+        constexpr int KD = 8;   // dims handled inside one launch (after merging)
+        constexpr int MAXT = 6; // tiled dims
+        constexpr int NT = 256; // threads per CTA
+        constexpr int EPT = 8;  // slots (elements of a tile) per thread
+
+        struct PermParams {
+            int nd, nt, tile_elems, smem_elems;
+            unsigned ntiles;
+            int size[KD];
+            int te[KD];
+            unsigned ntile[KD];
+            unsigned delta[KD]; // gridDim.x decomposed on the tile grid
+            long long tsstride[KD], tdstride[KD]; // te*stride: jump between tiles
+            int tdim[MAXT];                       // tiled dims, destination order
+            int text[MAXT];                       // their tile extents
+            int sord[MAXT];                       // positions in tdim[], sorted by source stride
+            int smem_stride[MAXT];
+            long long tss[MAXT], tds[MAXT]; // element strides of the tiled dims
+        };
+
+        // ---- element functors -----------------------------------------------------------------
+
+        template <typename T> struct is_cplx { static constexpr bool value = false; };
+        template <> struct is_cplx<float2> { static constexpr bool value = true; };
+        template <> struct is_cplx<double2> { static constexpr bool value = true; };
+
+        __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+        __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+        __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+        __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+        __device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+        __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+        // alpha * x in T, each real operation rounded once (no contraction into FMA)
+        __device__ __forceinline__ float scale(float a, float x) { return mul_rn(a, x); }
+        __device__ __forceinline__ double scale(double a, double x) { return mul_rn(a, x); }
+        __device__ __forceinline__ int scale(int a, int x) { return a * x; }
+        __device__ __forceinline__ float2 scale(float2 a, float2 x) {
+            return make_float2(sub_rn(mul_rn(a.x, x.x), mul_rn(a.y, x.y)),
+                               add_rn(mul_rn(a.x, x.y), mul_rn(a.y, x.x)));
+        }
+        __device__ __forceinline__ double2 scale(double2 a, double2 x) {
+            return make_double2(sub_rn(mul_rn(a.x, x.x), mul_rn(a.y, x.y)),
+                                add_rn(mul_rn(a.x, x.y), mul_rn(a.y, x.x)));
+        }
+
+        template <typename Q, typename T> struct Cvt;
+        template <typename T> struct Cvt<T, T> {
+            __device__ static __forceinline__ T to(T x) { return x; }
+        };
+        template <> struct Cvt<double, float> {
+            __device__ static __forceinline__ double to(float x) { return (double)x; }
+        };
+        template <> struct Cvt<float, double> {
+            __device__ static __forceinline__ float to(double x) { return __double2float_rn(x); }
+        };
+        template <> struct Cvt<double2, float2> {
+            __device__ static __forceinline__ double2 to(float2 x) {
+                return make_double2((double)x.x, (double)x.y);
+            }
+        };
+        template <> struct Cvt<float2, double2> {
+            __device__ static __forceinline__ float2 to(double2 x) {
+                return make_float2(__double2float_rn(x.x), __double2float_rn(x.y));
+            }
+        };
+
+        // the wider of two element types (C's usual arithmetic conversions for `w += x`)
+        template <typename Q, typename T> struct Wider { using type = Q; };
+        template <> struct Wider<float, double> { using type = double; };
+        template <> struct Wider<float2, double2> { using type = double2; };
+
+        __device__ __forceinline__ float plus(float a, float b) { return add_rn(a, b); }
+        __device__ __forceinline__ double plus(double a, double b) { return add_rn(a, b); }
+        __device__ __forceinline__ int plus(int a, int b) { return a + b; }
+        __device__ __forceinline__ float2 plus(float2 a, float2 b) {
+            return make_float2(add_rn(a.x, b.x), add_rn(a.y, b.y));
+        }
+        __device__ __forceinline__ double2 plus(double2 a, double2 b) {
+            return make_double2(add_rn(a.x, b.x), add_rn(a.y, b.y));
+        }
+
+        /// w = Q(alpha*x)   or   w = Q(W(w) + W(alpha*x)); `scale` and `add` are uniform run-time flags
+        template <typename T_, typename Q_> struct ElemOp {
+            using T = T_;
+            using Q = Q_;
+            T alpha;
+            bool scale_, add_;
+            __device__ __forceinline__ bool add() const { return add_; }
+            __device__ __forceinline__ Q apply(T x) const {
+                if (scale_) x = scale(alpha, x);
+                return Cvt<Q, T>::to(x);
+            }
+            __device__ __forceinline__ Q combine(Q old, T x) const {
+                if (scale_) x = scale(alpha, x);
+                using W = typename Wider<Q, T>::type;
+                return Cvt<Q, W>::to(plus(Cvt<W, Q>::to(old), Cvt<W, T>::to(x)));
+            }
+        };
+
+        /// Raw move of 4, 8 or 16 bytes
+        template <typename V> struct MoveOp {
+            using T = V;
+            using Q = V;
+            __device__ __forceinline__ constexpr bool add() const { return false; }
+            __device__ __forceinline__ V apply(V x) const { return x; }
+            __device__ __forceinline__ V combine(V, V x) const { return x; }
+        };
+
+        // ---- the kernel -------------------------------------------------------------------------
+
+        template <int N> struct SlotState {
+            unsigned so[N], dof[N], sp[N]; // element offsets inside the tile; sp = ld<<16 | st
+        };
+
+        /// Decompose slot index e following the enumeration `ord` (positions in tdim[]).
+        /// Returns false if e is outside the tile.
+        __device__ __forceinline__ void slot_coords(const PermParams &p, unsigned e,
+                                                    const int *ord, int c[MAXT]) {
+#pragma unroll
+            for (int q = 0; q < MAXT; ++q) c[q] = 0;
+#pragma unroll
+            for (int q = 0; q < MAXT; ++q) {
+                if (q < p.nt) {
+                    const int t = ord[q];
+                    const unsigned ext = (unsigned)p.text[t];
+                    const int v = (int)(e % ext);
+                    e /= ext;
+                    // c[t] = v without dynamic register indexing
+#pragma unroll
+                    for (int j = 0; j < MAXT; ++j)
+                        if (j == t) c[j] = v;
+                }
+            }
+        }
+
+        template <class Op, bool SMEM>
+        __global__ void __launch_bounds__(NT, 2)
+            permute_kernel(const __grid_constant__ PermParams p,
+                           const typename Op::T *__restrict__ src, typename Op::Q *dst, Op op) {
+            using T = typename Op::T;
+            using Q = typename Op::Q;
+            extern __shared__ __align__(16) unsigned char smem_raw[];
+            T *smem = reinterpret_cast<T *>(smem_raw);
+
+            const unsigned tid = threadIdx.x;
+            int dord[MAXT];
+#pragma unroll
+            for (int q = 0; q < MAXT; ++q) dord[q] = q;
+
+            // ---- per-slot maps, computed once -------------------------------------------------
+            unsigned so[EPT], dof[EPT], sp[EPT];
+            unsigned live = 0; // bit k set: slot k is inside the tile
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) {
+                const unsigned e = tid + k * NT;
+                so[k] = dof[k] = sp[k] = 0;
+                if (e < (unsigned)p.tile_elems) {
+                    live |= 1u << k;
+                    int c[MAXT];
+                    // store phase: destination enumeration
+                    slot_coords(p, e, dord, c);
+                    long long d = 0, s = 0;
+                    int pos = 0;
+#pragma unroll
+                    for (int q = 0; q < MAXT; ++q)
+                        if (q < p.nt) {
+                            d += c[q] * p.tds[q];
+                            s += c[q] * p.tss[q];
+                            pos += c[q] * p.smem_stride[q];
+                        }
+                    dof[k] = (unsigned)d;
+                    if (SMEM) {
+                        sp[k] = (unsigned)pos;
+                        // load phase: source enumeration
+                        slot_coords(p, e, p.sord, c);
+                        s = 0, pos = 0;
+#pragma unroll
+                        for (int q = 0; q < MAXT; ++q)
+                            if (q < p.nt) {
+                                s += c[q] * p.tss[q];
+                                pos += c[q] * p.smem_stride[q];
+                            }
+                        sp[k] |= (unsigned)pos << 16;
+                    }
+                    so[k] = (unsigned)s;
+                }
+            }
+
+            // ---- tile loop ----------------------------------------------------------------------
+            unsigned tc[KD];
+            {
+                unsigned t = blockIdx.x;
+#pragma unroll
+                for (int d = 0; d < KD; ++d) {
+                    tc[d] = 0;
+                    if (d < p.nd) {
+                        tc[d] = t % p.ntile[d];
+                        t /= p.ntile[d];
+                    }
+                }
+            }
+            for (unsigned tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                long long sbase = 0, dbase = 0;
+                bool full = true;
+#pragma unroll
+                for (int d = 0; d < KD; ++d)
+                    if (d < p.nd) {
+                        sbase += tc[d] * p.tsstride[d];
+                        dbase += tc[d] * p.tdstride[d];
+                        full = full && ((tc[d] + 1) * (unsigned)p.te[d] <= (unsigned)p.size[d]);
+                    }
+                const T *s = src + sbase;
+                Q *w = dst + dbase;
+
+                if (full) {
+                    if (SMEM) {
+                        T r[EPT];
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if (live >> k & 1) r[k] = s[so[k]];
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if (live >> k & 1) smem[sp[k] >> 16] = r[k];
+                        __syncthreads();
+                        if (op.add()) {
+                            Q o[EPT];
+#pragma unroll
+                            for (int k = 0; k < EPT; ++k)
+                                if (live >> k & 1) o[k] = w[dof[k]];
+#pragma unroll
+                            for (int k = 0; k < EPT; ++k)
+                                if (live >> k & 1)
+                                    w[dof[k]] = op.combine(o[k], smem[sp[k] & 0xffffu]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < EPT; ++k)
+                                if (live >> k & 1) w[dof[k]] = op.apply(smem[sp[k] & 0xffffu]);
+                        }
+                        __syncthreads();
+                    } else {
+                        T r[EPT];
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if (live >> k & 1) r[k] = s[so[k]];
+                        if (op.add()) {
+                            Q o[EPT];
+#pragma unroll
+                            for (int k = 0; k < EPT; ++k)
+                                if (live >> k & 1) o[k] = w[dof[k]];
+#pragma unroll
+                            for (int k = 0; k < EPT; ++k)
+                                if (live >> k & 1) w[dof[k]] = op.combine(o[k], r[k]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < EPT; ++k)
+                                if (live >> k & 1) w[dof[k]] = op.apply(r[k]);
+                        }
+                    }
+                } else {
+                    // boundary tile: recompute coordinates to mask what falls outside the box
+                    int lim[MAXT];
+#pragma unroll
+                    for (int q = 0; q < MAXT; ++q) {
+                        lim[q] = 1;
+                        if (q < p.nt) {
+                            const int d = p.tdim[q];
+                            unsigned tcd = 0;
+#pragma unroll
+                            for (int dd = 0; dd < KD; ++dd)
+                                if (dd == d) tcd = tc[dd];
+                            lim[q] = min(p.text[q], p.size[d] - (int)(tcd * (unsigned)p.te[d]));
+                        }
+                    }
+                    auto inside = [&](unsigned e, const int *ord) {
+                        int c[MAXT];
+                        slot_coords(p, e, ord, c);
+                        bool ok = true;
+#pragma unroll
+                        for (int q = 0; q < MAXT; ++q) ok = ok && (c[q] < lim[q]);
+                        return ok;
+                    };
+                    if (SMEM) {
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if ((live >> k & 1) && inside(tid + k * NT, p.sord))
+                                smem[sp[k] >> 16] = s[so[k]];
+                        __syncthreads();
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if ((live >> k & 1) && inside(tid + k * NT, dord)) {
+                                const T x = smem[sp[k] & 0xffffu];
+                                w[dof[k]] = op.add() ? op.combine(w[dof[k]], x) : op.apply(x);
+                            }
+                        __syncthreads();
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if ((live >> k & 1) && inside(tid + k * NT, dord)) {
+                                const T x = s[so[k]];
+                                w[dof[k]] = op.add() ? op.combine(w[dof[k]], x) : op.apply(x);
+                            }
+                    }
+                }
+
+                // next tile of this CTA: tc += delta with carries
+                unsigned carry = 0;
+#pragma unroll
+                for (int d = 0; d < KD; ++d)
+                    if (d < p.nd) {
+                        unsigned v = tc[d] + p.delta[d] + carry;
+                        carry = v >= p.ntile[d] ? 1u : 0u;
+                        if (carry) v -= p.ntile[d];
+                        tc[d] = v;
+                    }
+            }
+        }
+
+        /// Zero fill of a strided box (direct variant without source)
+        template <class V>
+        __global__ void __launch_bounds__(NT)
+            zero_kernel(const __grid_constant__ PermParams p, V *dst) {
+            const unsigned tid = threadIdx.x;
+            int dord[MAXT];
+#pragma unroll
+            for (int q = 0; q < MAXT; ++q) dord[q] = q;
+            V zero;
+            memset(&zero, 0, sizeof(V));
+            for (unsigned tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+                long long dbase = 0;
+                unsigned t = tile;
+                int lim[MAXT];
+                unsigned tcs[KD];
+#pragma unroll
+                for (int d = 0; d < KD; ++d) {
+                    tcs[d] = 0;
+                    if (d < p.nd) {
+                        tcs[d] = t % p.ntile[d];
+                        t /= p.ntile[d];
+                        dbase += tcs[d] * p.tdstride[d];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < MAXT; ++q) {
+                    lim[q] = 1;
+                    if (q < p.nt) {
+                        const int d = p.tdim[q];
+                        unsigned tcd = 0;
+#pragma unroll
+                        for (int dd = 0; dd < KD; ++dd)
+                            if (dd == d) tcd = tcs[dd];
+                        lim[q] = min(p.text[q], p.size[d] - (int)(tcd * (unsigned)p.te[d]));
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < EPT; ++k) {
+                    const unsigned e = tid + k * NT;
+                    if (e < (unsigned)p.tile_elems) {
+                        int c[MAXT];
+                        slot_coords(p, e, dord, c);
+                        bool ok = true;
+                        long long d = 0;
+#pragma unroll
+                        for (int q = 0; q < MAXT; ++q) {
+                            ok = ok && (c[q] < lim[q]);
+                            if (q < p.nt) d += c[q] * p.tds[q];
+                        }
+                        if (ok) dst[dbase + d] = zero;
+                    }
+                }
+            }
+        }
+
+        // ---- host side: canonical form, tiling, launch --------------------------------------------
+
+        struct Canon {
+            int nd = 0;
+            std::vector<int> size;
+            std::vector<int64_t> ss, ds;
+            int64_t soff = 0, doff = 0;
+        };
+
+        Canon canonicalize(const sbk_box_desc &b, bool has_src) {
+            Canon c;
+            c.soff = b.soff, c.doff = b.doff;
+            std::vector<int> idx;
+            for (int k = 0; k < b.nd; ++k) {
+                if (b.size[k] <= 0) {
+                    c.nd = -1; // empty
+                    return c;
+                }
+                if (b.size[k] > 1) idx.push_back(k);
+            }
+            std::stable_sort(idx.begin(), idx.end(),
+                             [&](int x, int y) { return b.dstride[x] < b.dstride[y]; });
+            for (int k : idx) {
+                const int64_t ss = has_src ? b.sstride[k] : 0, ds = b.dstride[k];
+                if (!c.size.empty()) {
+                    const int64_t n = c.size.back();
+                    if (c.ds.back() * n == ds && c.ss.back() * n == ss &&
+                        n * (int64_t)b.size[k] < (1ll << 30)) {
+                        c.size.back() *= b.size[k];
+                        continue;
+                    }
+                }
+                c.size.push_back(b.size[k]);
+                c.ss.push_back(ss);
+                c.ds.push_back(ds);
+            }
+            c.nd = (int)c.size.size();
+            return c;
+        }
+
+        struct Tiling {
+            std::vector<int> te;
+            int64_t run_d = 1, run_s = 1, total = 1;
+        };
+
+        /// Greedy tile: cover `want_d` contiguous destination elements and `want_s` contiguous
+        /// source elements.
+        Tiling build_tile(const Canon &c, const std::vector<int> &sorder, int64_t want_d,
+                          int64_t want_s) {
+            Tiling t;
+            t.te.assign(c.nd, 1);
+            int64_t acc = 1;
+            for (int d = 0; d < c.nd && acc < want_d; ++d) {
+                if (d == 0 ? false : c.ds[d] != c.ds[d - 1] * c.size[d - 1]) break;
+                const int64_t need = (want_d + acc - 1) / acc;
+                const int ext = (int)std::min<int64_t>(c.size[d], need);
+                t.te[d] = ext;
+                acc *= ext;
+                if (ext < c.size[d]) break;
+            }
+            acc = 1;
+            for (size_t q = 0; q < sorder.size() && acc < want_s; ++q) {
+                const int d = sorder[q];
+                if (q > 0 && c.ss[d] != c.ss[sorder[q - 1]] * c.size[sorder[q - 1]]) break;
+                if (q > 0 && t.te[sorder[q - 1]] < c.size[sorder[q - 1]]) break;
+                const int64_t need = (want_s + acc - 1) / acc;
+                const int ext = std::max<int>(t.te[d], (int)std::min<int64_t>(c.size[d], need));
+                t.te[d] = ext;
+                acc *= ext;
+                if (ext < c.size[d]) break;
+            }
+            // actual runs
+            t.run_d = 1;
+            for (int d = 0; d < c.nd; ++d) {
+                if (d > 0 && (c.ds[d] != c.ds[d - 1] * c.size[d - 1] || t.te[d - 1] < c.size[d - 1]))
+                    break;
+                t.run_d *= t.te[d];
+            }
+            t.run_s = 1;
+            for (size_t q = 0; q < sorder.size(); ++q) {
+                const int d = sorder[q];
+                if (q > 0) {
+                    const int pd = sorder[q - 1];
+                    if (c.ss[d] != c.ss[pd] * c.size[pd] || t.te[pd] < c.size[pd]) break;
+                }
+                t.run_s *= t.te[d];
+            }
+            t.total = 1;
+            for (int d = 0; d < c.nd; ++d) t.total *= t.te[d];
+            return t;
+        }
+
+        struct LaunchPlan {
+            PermParams p;
+            bool smem = false;
+            int es = 0; // element size in bytes seen by the kernel
+            int64_t run_d = 0, run_s = 0;
+            bool empty = false;
+        };
+
+        /// Fill PermParams for a canonical box; `es` = bytes per element, `max_tile` = NT*EPT.
+        LaunchPlan plan_launch(const Canon &c, int es, int max_tile, bool has_src) {
+            LaunchPlan lp;
+            lp.es = es;
+            PermParams &p = lp.p;
+            memset(&p, 0, sizeof p);
+            p.nd = std::max(c.nd, 1);
+            Canon cc = c;
+            if (c.nd == 0) { // single element
+                cc.nd = 1;
+                cc.size = {1};
+                cc.ss = {1};
+                cc.ds = {1};
+            }
+            std::vector<int> sorder(cc.nd);
+            std::iota(sorder.begin(), sorder.end(), 0);
+            if (has_src)
+                std::stable_sort(sorder.begin(), sorder.end(),
+                                 [&](int x, int y) { return cc.ss[x] < cc.ss[y]; });
+            // The fastest source dim must be contiguous for a source run to exist at all
+            const bool src_contig = has_src && cc.ss[sorder[0]] == 1;
+            const bool dst_contig = cc.ds[0] == 1;
+
+            // candidate search: maximise covered bytes per side (capped at 512 B), then tile size
+            Tiling best;
+            double best_score = -1;
+            for (int64_t wd = 1; wd <= max_tile; wd *= 2)
+                for (int64_t ws = 1; ws <= max_tile; ws *= 2) {
+                    Tiling t = build_tile(cc, sorder, dst_contig ? wd : 1, src_contig ? ws : 1);
+                    if (t.total > max_tile) continue;
+                    // count tiled dims
+                    int nt = 0;
+                    for (int d = 0; d < cc.nd; ++d) nt += t.te[d] > 1;
+                    if (nt > MAXT) continue;
+                    const double sd = (double)std::min<int64_t>(t.run_d * es, 512);
+                    const double ssrc = has_src ? (double)std::min<int64_t>(t.run_s * es, 512) : 512;
+                    const double score = (sd + ssrc) * 1e6 + (double)t.total;
+                    if (score > best_score) best_score = score, best = t;
+                }
+            // grow small tiles along further destination dims so that a CTA has enough in flight
+            for (int d = 0; d < cc.nd; ++d) {
+                while (best.te[d] < cc.size[d] && best.total * 2 <= max_tile) {
+                    int nt = 0;
+                    for (int k = 0; k < cc.nd; ++k) nt += best.te[k] > 1;
+                    if (best.te[d] == 1 && nt >= MAXT) break;
+                    const int ne = std::min(cc.size[d], best.te[d] * 2);
+                    if (best.total / best.te[d] * ne > max_tile) break;
+                    best.total = best.total / best.te[d] * ne;
+                    best.te[d] = ne;
+                }
+            }
+            // 32-bit in-tile offsets: shrink extents on huge-stride dims if needed
+            for (;;) {
+                int64_t ms = 0, md = 0;
+                int worst = -1;
+                int64_t worst_v = 0;
+                for (int d = 0; d < cc.nd; ++d) {
+                    const int64_t vs = (best.te[d] - 1) * cc.ss[d], vd = (best.te[d] - 1) * cc.ds[d];
+                    ms += vs, md += vd;
+                    if (std::max(vs, vd) > worst_v) worst_v = std::max(vs, vd), worst = d;
+                }
+                if (ms < (1ll << 31) && md < (1ll << 31)) break;
+                best.total /= best.te[worst];
+                best.te[worst] = std::max(1, best.te[worst] / 2);
+                best.total *= best.te[worst];
+            }
+
+            int64_t ntiles = 1;
+            for (int d = 0; d < cc.nd; ++d) {
+                p.size[d] = cc.size[d];
+                p.te[d] = best.te[d];
+                p.ntile[d] = (unsigned)((cc.size[d] + best.te[d] - 1) / best.te[d]);
+                p.tsstride[d] = (long long)best.te[d] * cc.ss[d];
+                p.tdstride[d] = (long long)best.te[d] * cc.ds[d];
+                ntiles *= p.ntile[d];
+            }
+            if (ntiles >= (1ll << 31)) throw std::runtime_error("permute copy: too many tiles");
+            p.ntiles = (unsigned)ntiles;
+            p.nt = 0;
+            for (int d = 0; d < cc.nd; ++d)
+                if (best.te[d] > 1) {
+                    p.tdim[p.nt] = d;
+                    p.text[p.nt] = best.te[d];
+                    p.tss[p.nt] = cc.ss[d];
+                    p.tds[p.nt] = cc.ds[d];
+                    ++p.nt;
+                }
+            p.tile_elems = (int)best.total;
+            // source enumeration order of the tiled dims
+            std::vector<int> so(p.nt);
+            std::iota(so.begin(), so.end(), 0);
+            std::stable_sort(so.begin(), so.end(), [&](int x, int y) { return p.tss[x] < p.tss[y]; });
+            bool same_order = true;
+            for (int q = 0; q < p.nt; ++q) {
+                p.sord[q] = so[q];
+                if (so[q] != q) same_order = false;
+            }
+            lp.smem = has_src && !same_order;
+            // shared memory layout: destination order, odd stride for the source-fastest dim
+            int stride = 1;
+            for (int q = 0; q < p.nt; ++q) {
+                if (lp.smem && q > 0 && q == so[0] && stride % 2 == 0) stride += 1;
+                p.smem_stride[q] = stride;
+                stride *= p.text[q];
+            }
+            p.smem_elems = lp.smem ? stride : 0;
+            if (p.smem_elems > 65535) throw std::runtime_error("permute copy: tile too large");
+            lp.run_d = best.run_d, lp.run_s = best.run_s;
+            return lp;
+        }
+
+        void set_delta(PermParams &p, unsigned grid) {
+            unsigned t = grid;
+            for (int d = 0; d < KD; ++d) {
+                p.delta[d] = 0;
+                if (d < p.nd) {
+                    p.delta[d] = t % p.ntile[d];
+                    t /= p.ntile[d];
+                }
+            }
+        }
+
+        struct DevInfo {
+            int sms = 0;
+        };
+        DevInfo &dev_info(int device) {
+            static DevInfo info[64];
+            if (info[device].sms == 0) {
+                cudaDeviceProp prop;
+                cuda_check(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+                info[device].sms = prop.multiProcessorCount;
+            }
+            return info[device];
+        }
+
+        template <class Kernel> int resident_ctas(Kernel k, size_t smem_bytes) {
+            if (smem_bytes > 48 * 1024)
+                cuda_check(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem_bytes),
+                           "cudaFuncSetAttribute");
+            int n = 0;
+            cuda_check(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k, NT, smem_bytes),
+                       "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+            return std::max(n, 1);
+        }
+
+        template <class Op>
+        void launch_perm(LaunchPlan &lp, const void *src, void *dst, Op op, int device,
+                         cudaStream_t stream) {
+            using T = typename Op::T;
+            using Q = typename Op::Q;
+            const size_t smem_bytes = (size_t)lp.p.smem_elems * sizeof(T);
+            auto go = [&](auto kernel) {
+                // resident CTAs per SM for this kernel, cached by dynamic shared-memory size
+                static std::map<size_t, int> ctas;
+                auto it = ctas.find(smem_bytes);
+                if (it == ctas.end()) it = ctas.emplace(smem_bytes, resident_ctas(kernel, smem_bytes)).first;
+                const unsigned grid = (unsigned)std::min<int64_t>(
+                    lp.p.ntiles, (int64_t)dev_info(device).sms * it->second);
+                set_delta(lp.p, grid);
+                kernel<<<grid, NT, smem_bytes, stream>>>(lp.p, (const T *)src, (Q *)dst, op);
+                count_launch();
+                cuda_check(cudaGetLastError(), "permute_kernel launch");
+            };
+            if (lp.smem)
+                go(permute_kernel<Op, true>);
+            else
+                go(permute_kernel<Op, false>);
+        }
+
+        template <class V>
+        void launch_zero(LaunchPlan &lp, void *dst, int device, cudaStream_t stream) {
+            const unsigned grid =
+                (unsigned)std::min<int64_t>(lp.p.ntiles, (int64_t)dev_info(device).sms * 8);
+            zero_kernel<V><<<grid, NT, 0, stream>>>(lp.p, (V *)dst);
+            count_launch();
+            cuda_check(cudaGetLastError(), "zero_kernel launch");
+        }
+
+        int max_tile_for(int) { return NT * EPT; }
+
+        /// Widen the element when the fastest dim is shared, contiguous and aligned
+        int promote(Canon &c, int es, const void *src, const void *dst, bool has_src) {
+            if (c.nd < 1 || c.ds[0] != 1 || (has_src && c.ss[0] != 1)) return es;
+            int f = 16 / es;
+            for (; f > 1; f /= 2) {
+                bool ok = true;
+                if (c.size[0] % f) ok = false;
+                for (int d = 1; ok && d < c.nd; ++d)
+                    if (c.ds[d] % f || (has_src && c.ss[d] % f)) ok = false;
+                if (ok && (c.doff % f || (has_src && c.soff % f))) ok = false;
+                if (ok && ((uintptr_t)dst + (uintptr_t)c.doff * es) % ((size_t)f * es)) ok = false;
+                if (ok && has_src && ((uintptr_t)src + (uintptr_t)c.soff * es) % ((size_t)f * es))
+                    ok = false;
+                if (ok) break;
+            }
+            if (f <= 1) return es;
+            c.size[0] /= f;
+            for (int d = 1; d < c.nd; ++d) {
+                c.ds[d] /= f;
+                if (has_src) c.ss[d] /= f;
+            }
+            c.doff /= f;
+            if (has_src) c.soff /= f;
+            // the widened dim may now merge with the next one, or vanish
+            if (c.size[0] == 1) {
+                c.size.erase(c.size.begin());
+                c.ss.erase(c.ss.begin());
+                c.ds.erase(c.ds.begin());
+                c.nd--;
+            }
+            return es * f;
+        }
+
+        template <typename T> T make_elem(const double *a);
+        template <> float make_elem<float>(const double *a) { return (float)a[0]; }
+        template <> double make_elem<double>(const double *a) { return a[0]; }
+        template <> int make_elem<int>(const double *a) { return (int)a[0]; }
+        template <> float2 make_elem<float2>(const double *a) {
+            return make_float2((float)a[0], (float)a[1]);
+        }
+        template <> double2 make_elem<double2>(const double *a) { return make_double2(a[0], a[1]); }
+
+        template <typename T, typename Q>
+        void launch_typed(LaunchPlan &lp, const void *src, void *dst, const double *alpha,
+                          bool scale, bool add, int device, cudaStream_t stream) {
+            launch_perm<ElemOp<T, Q>>(lp, src, dst, {make_elem<T>(alpha), scale, add}, device,
+                                           stream);
+        }
+
+        struct Decision {
+            enum { Empty, Zero, Move, Typed } kind = Empty;
+            int es = 0;
+            Canon canon;
+        };
+
+        int dtype_size(int dt) {
+            switch (dt) {
+            case SBB_F32: return 4;
+            case SBB_F64: return 8;
+            case SBB_C64: return 8;
+            case SBB_C128: return 16;
+            case SBB_I32: return 4;
+            default: throw std::runtime_error("unsupported element type");
+            }
+        }
+
+        bool convertible(int dt0, int dt1) {
+            if (dt0 == dt1) return true;
+            return (dt0 == SBB_F32 && dt1 == SBB_F64) || (dt0 == SBB_F64 && dt1 == SBB_F32) ||
+                   (dt0 == SBB_C64 && dt1 == SBB_C128) || (dt0 == SBB_C128 && dt1 == SBB_C64);
+        }
+
+        /// Run one box of at most KD (canonical) dims
+        void run_box(const Canon &c0, const void *src, int dt0, void *dst, int dt1,
+                     const double *alpha, bool add, int device, cudaStream_t stream,
+                     std::string *describe) {
+            const bool is_zero = alpha[0] == 0 && (alpha[1] == 0 || dt0 == SBB_F32 ||
+                                                   dt0 == SBB_F64 || dt0 == SBB_I32);
+            const bool is_one = alpha[0] == 1 && (alpha[1] == 0 || dt0 == SBB_F32 ||
+                                                  dt0 == SBB_F64 || dt0 == SBB_I32);
+            if (is_zero && add) return;
+            Canon c = c0;
+            std::stringstream ds;
+            if (is_zero) {
+                int es = promote(c, dtype_size(dt1), nullptr, dst, false);
+                LaunchPlan lp = plan_launch(c, es, NT * EPT, false);
+                if (describe) {
+                    ds << "zero es=" << es << " tile=" << lp.p.tile_elems << " ntiles=" << lp.p.ntiles;
+                    *describe = ds.str();
+                    return;
+                }
+                char *d = (char *)dst + c.doff * es;
+                if (es == 16) launch_zero<uint4>(lp, d, device, stream);
+                else if (es == 8) launch_zero<uint2>(lp, d, device, stream);
+                else launch_zero<unsigned>(lp, d, device, stream);
+                return;
+            }
+            if (dt0 == dt1 && is_one && !add) {
+                int es = promote(c, dtype_size(dt0), src, dst, true);
+                LaunchPlan lp = plan_launch(c, es, max_tile_for(es), true);
+                if (describe) {
+                    ds << (lp.smem ? "move tiled" : "move direct") << " es=" << es
+                       << " tile=" << lp.p.tile_elems << " ntiles=" << lp.p.ntiles
+                       << " run_dst=" << lp.run_d * es << "B run_src=" << lp.run_s * es << "B nd="
+                       << lp.p.nd;
+                    *describe = ds.str();
+                    return;
+                }
+                const char *s = (const char *)src + c.soff * es;
+                char *d = (char *)dst + c.doff * es;
+                if (es == 16) launch_perm<MoveOp<uint4>>(lp, s, d, {}, device, stream);
+                else if (es == 8) launch_perm<MoveOp<uint2>>(lp, s, d, {}, device, stream);
+                else launch_perm<MoveOp<unsigned>>(lp, s, d, {}, device, stream);
+                return;
+            }
+            // typed path on native elements
+            const int es0 = dtype_size(dt0), es1 = dtype_size(dt1);
+            LaunchPlan lp = plan_launch(c, std::max(es0, es1), NT * EPT, true);
+            if (describe) {
+                ds << (lp.smem ? "typed tiled" : "typed direct") << " es=" << es0 << "->" << es1
+                   << " tile=" << lp.p.tile_elems << " ntiles=" << lp.p.ntiles
+                   << " scale=" << !is_one << " add=" << add;
+                *describe = ds.str();
+                return;
+            }
+            const char *s = (const char *)src + c.soff * es0;
+            char *d = (char *)dst + c.doff * es1;
+            const bool scale = !is_one;
+#define SBB_TYPED(DT0, DT1, T, Q)                                                                  \
+    if (dt0 == DT0 && dt1 == DT1) {                                                                \
+        launch_typed<T, Q>(lp, s, d, alpha, scale, add, device, stream);                           \
+        return;                                                                                    \
+    }
+            SBB_TYPED(SBB_F32, SBB_F32, float, float)
+            SBB_TYPED(SBB_F64, SBB_F64, double, double)
+            SBB_TYPED(SBB_C64, SBB_C64, float2, float2)
+            SBB_TYPED(SBB_C128, SBB_C128, double2, double2)
+            SBB_TYPED(SBB_I32, SBB_I32, int, int)
+            SBB_TYPED(SBB_F32, SBB_F64, float, double)
+            SBB_TYPED(SBB_F64, SBB_F32, double, float)
+            SBB_TYPED(SBB_C64, SBB_C128, float2, double2)
+            SBB_TYPED(SBB_C128, SBB_C64, double2, float2)
+#undef SBB_TYPED
+            throw std::runtime_error("permute copy: unsupported type combination");
+        }
+
+    } // namespace
+
+    void permute_copy(const sbk_box_desc &box, const void *src, int dt0, void *dst, int dt1,
+                      const double *alpha, bool add, int device, cudaStream_t stream,
+                      std::string *describe) {
+        if (box.nd < 0 || box.nd > SBK_MAX_DIMS) throw std::runtime_error("permute copy: bad nd");
+        if (!convertible(dt0, dt1))
+            throw std::runtime_error("permute copy: unsupported type combination");
+        const bool is_zero = alpha[0] == 0 && (alpha[1] == 0 || dt0 == SBB_F32 || dt0 == SBB_F64 ||
+                                               dt0 == SBB_I32);
+        Canon c = canonicalize(box, !is_zero);
+        if (c.nd < 0) {
+            if (describe) *describe = "empty";
+            return;
+        }
+        if (c.nd <= KD) {
+            run_box(c, src, dt0, dst, dt1, alpha, add, device, stream, describe);
+            return;
+        }
+        // More than KD irreducible dims: iterate over the slowest ones on the host
+        const int outer = c.nd - KD;
+        std::vector<int> idx(outer, 0);
+        for (;;) {
+            Canon sub = c;
+            sub.nd = KD;
+            sub.size.resize(KD), sub.ss.resize(KD), sub.ds.resize(KD);
+            for (int k = 0; k < outer; ++k) {
+                sub.soff += idx[k] * c.ss[KD + k];
+                sub.doff += idx[k] * c.ds[KD + k];
+            }
+            run_box(sub, src, dt0, dst, dt1, alpha, add, device, stream, describe);
+            if (describe) return;
+            int k = 0;
+            for (; k < outer; ++k) {
+                if (++idx[k] < c.size[KD + k]) break;
+                idx[k] = 0;
+            }
+            if (k == outer) break;
+        }
+    }
+
+} // namespace sbb

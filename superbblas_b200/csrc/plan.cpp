@@ -1,0 +1,315 @@
+// Copy planner. See plan.hpp.
+#include "plan.hpp"
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <sstream>
+
+namespace sbb {
+
+    void check_copy_args(const CopyArgs &a) {
+        auto bad_len = [](const char *name, int n) {
+            std::stringstream ss;
+            ss << "The length of the order should match the template argument; argument `" << name
+               << "` should have length " << n;
+            throw std::runtime_error(ss.str());
+        };
+        if ((int)a.o0.size() != a.nd0) bad_len("o0", a.nd0);
+        if ((int)a.o1.size() != a.nd1) bad_len("o1", a.nd1);
+        auto invalid = [] { throw std::runtime_error("Invalid copy operation"); };
+        auto unique = [](const std::string &o) {
+            for (size_t i = 0; i < o.size(); ++i)
+                if (o.find(o[i], i + 1) != std::string::npos) return false;
+            return true;
+        };
+        if (!unique(a.o0) || !unique(a.o1)) invalid();
+        for (int k = 0; k < a.nd0; ++k) {
+            if (a.size0[k] < 0 || a.size0[k] > a.dim0[k]) invalid();
+            if (a.size0[k] > 1 && a.o1.find(a.o0[k]) == std::string::npos) invalid();
+        }
+        if (volume(a.size0) != 0)
+            for (int m = 0; m < a.nd1; ++m) {
+                const auto k = a.o0.find(a.o1[m]);
+                const int s = k == std::string::npos ? 1 : a.size0[k];
+                if (s > a.dim1[m]) invalid();
+            }
+        if ((int)a.p0.size() != a.nranks * a.ncomp0 || (int)a.p1.size() != a.nranks * a.ncomp1)
+            throw std::runtime_error("wtf");
+    }
+
+    namespace {
+
+        /// All range-space boxes of (part ∩ range). `to_range[k]` = range dimension of the part's
+        /// k-th dimension or -1 (then the range has extent 1 there and only lfrom is recorded).
+        std::vector<RBox> part_boxes(const Box &part, const Coor &rfrom, const Coor &rsize,
+                                     const Coor &dim, const std::vector<int> &to_range,
+                                     int nrange) {
+            std::vector<RBox> out;
+            const int n = (int)part.from.size();
+            if (part.empty()) return out;
+            std::vector<std::vector<Piece>> pieces(n);
+            for (int k = 0; k < n; ++k) {
+                pieces[k] = ring_pieces(part.from[k], part.size[k], rfrom[k], rsize[k], dim[k]);
+                if (pieces[k].empty()) return out;
+            }
+            std::vector<int> idx(n, 0);
+            for (;;) {
+                RBox b;
+                b.u.assign(nrange, 0);
+                b.len.assign(nrange, 1);
+                b.lfrom.resize(n);
+                for (int k = 0; k < n; ++k) {
+                    const Piece &pc = pieces[k][idx[k]];
+                    b.lfrom[k] = pc.local;
+                    if (to_range[k] >= 0) b.u[to_range[k]] = pc.u, b.len[to_range[k]] = pc.len;
+                }
+                out.push_back(std::move(b));
+                int k = 0;
+                for (; k < n; ++k) {
+                    if (++idx[k] < (int)pieces[k].size()) break;
+                    idx[k] = 0;
+                }
+                if (k == n) break;
+            }
+            return out;
+        }
+
+        int64_t align_up(int64_t x, int a) { return a <= 1 ? x : (x + a - 1) / a * a; }
+
+    }
+
+    std::shared_ptr<const CopyPlan> make_copy_plan(const CopyArgs &a) {
+        check_copy_args(a);
+        auto plan = std::make_shared<CopyPlan>();
+        plan->nranks = a.nranks;
+        plan->rank = a.rank;
+        plan->send_elems.assign(a.nranks, 0);
+        plan->recv_elems.assign(a.nranks, 0);
+        const int n0 = a.nd0, n1 = a.nd1, me = a.rank;
+
+        // Range space = destination label order
+        std::vector<int> src_to_range(n0, -1), range_to_src(n1, -1), dst_to_range(n1);
+        Coor size1(n1, 1);
+        for (int m = 0; m < n1; ++m) {
+            dst_to_range[m] = m;
+            const auto k = a.o0.find(a.o1[m]);
+            if (k != std::string::npos) {
+                src_to_range[k] = m;
+                range_to_src[m] = (int)k;
+                size1[m] = a.size0[k];
+            }
+        }
+        if (volume(a.size0) == 0) return plan;
+        if (a.add && a.alpha_is_zero) return plan;
+
+        const int P0 = (int)a.p0.size(), P1 = (int)a.p1.size();
+
+        // Source boxes of every part (needed by every rank to agree on who sends what)
+        std::vector<std::vector<RBox>> S(P0);
+        std::vector<std::vector<int64_t>> sstr(P0);
+        if (!a.alpha_is_zero)
+            for (int i = 0; i < P0; ++i) {
+                S[i] = part_boxes(a.p0[i], a.from0, a.size0, a.dim0, src_to_range, n1);
+                sstr[i] = get_strides(a.p0[i].size, a.co);
+            }
+
+        // Order in which the dimensions of an op are listed: destination order, fastest first
+        std::vector<int> dim_order(n1);
+        for (int m = 0; m < n1; ++m) dim_order[m] = a.co == FastToSlow ? m : n1 - 1 - m;
+
+        // per (sender, receiver) running offsets inside the message, for the pairs that involve me
+        std::vector<int64_t> wire_out(a.nranks, 0), wire_in(a.nranks, 0);
+
+        auto emit = [&](int i, int j, const RBox &sb, const RBox &db, const Coor &u,
+                        const Coor &len, const std::vector<int64_t> &dstr) {
+            const int ri = i / a.ncomp0, rj = j / a.ncomp1;
+            if (ri != me && rj != me) return;
+            BoxOp op;
+            op.src_part = i, op.dst_part = j;
+            int64_t soff = 0, doff = 0;
+            for (int k = 0; k < n0; ++k) {
+                int l = sb.lfrom[k];
+                if (src_to_range[k] >= 0) l += u[src_to_range[k]] - sb.u[src_to_range[k]];
+                soff += (int64_t)l * sstr[i][k];
+            }
+            for (int m = 0; m < n1; ++m) doff += (int64_t)(db.lfrom[m] + u[m] - db.u[m]) * dstr[m];
+            for (int m : dim_order) {
+                if (len[m] == 1) continue;
+                op.size.push_back(len[m]);
+                op.sstride.push_back(range_to_src[m] >= 0 ? sstr[i][range_to_src[m]] : 0);
+                op.dstride.push_back(dstr[m]);
+            }
+            const int64_t vol = volume(len);
+            if (ri == me && rj == me) {
+                op.kind = BoxOp::Local;
+                op.src_comp = i % a.ncomp0, op.dst_comp = j % a.ncomp1;
+                op.soff = soff, op.doff = doff;
+            } else {
+                // compact, destination-ordered layout on the wire
+                std::vector<int64_t> wstr(op.size.size(), 1);
+                for (size_t d = 1; d < op.size.size(); ++d) wstr[d] = wstr[d - 1] * op.size[d - 1];
+                if (ri == me) {
+                    op.kind = BoxOp::Pack;
+                    op.peer = rj;
+                    op.src_comp = i % a.ncomp0;
+                    op.soff = soff;
+                    op.doff = wire_out[rj];
+                    op.dstride = wstr;
+                    wire_out[rj] = align_up(wire_out[rj] + vol, a.wire_align);
+                } else {
+                    op.kind = BoxOp::Unpack;
+                    op.peer = ri;
+                    op.dst_comp = j % a.ncomp1;
+                    op.doff = doff;
+                    op.soff = wire_in[ri];
+                    op.sstride = wstr;
+                    wire_in[ri] = align_up(wire_in[ri] + vol, a.wire_align);
+                }
+            }
+            plan->ops.push_back(std::move(op));
+        };
+
+        auto emit_zero = [&](int j, const RBox &db, const std::vector<int64_t> &dstr) {
+            if (j / a.ncomp1 != me) return;
+            BoxOp op;
+            op.kind = BoxOp::Zero;
+            op.dst_part = j, op.dst_comp = j % a.ncomp1;
+            int64_t doff = 0;
+            for (int m = 0; m < n1; ++m) doff += (int64_t)db.lfrom[m] * dstr[m];
+            op.doff = doff;
+            for (int m : dim_order) {
+                if (db.len[m] == 1) continue;
+                op.size.push_back(db.len[m]);
+                op.sstride.push_back(0);
+                op.dstride.push_back(dstr[m]);
+            }
+            plan->ops.push_back(std::move(op));
+        };
+
+        for (int j = 0; j < P1; ++j) {
+            const int rj = j / a.ncomp1;
+            std::vector<RBox> D = part_boxes(a.p1[j], a.from1, size1, a.dim1, dst_to_range, n1);
+            if (D.empty()) continue;
+            const auto dstr = get_strides(a.p1[j].size, a.co);
+
+            if (a.alpha_is_zero) { // Copy with alpha==0: zero the range, never read v0
+                for (const auto &db : D) emit_zero(j, db, dstr);
+                continue;
+            }
+
+            if (a.add) {
+                // every holder contributes, in ascending part order
+                for (int i = 0; i < P0; ++i)
+                    for (const auto &sb : S[i])
+                        for (const auto &db : D) {
+                            Coor u, len;
+                            if (intersect(sb, db, u, len)) emit(i, j, sb, db, u, len, dstr);
+                        }
+                continue;
+            }
+
+            // Copy: every destination element is written exactly once; holders on the destination's
+            // own rank are preferred (no traffic), then ascending part order. What nobody holds is
+            // zero-filled (the reference zeroes the whole range first, dist.h:2356-2382).
+            std::vector<int> pref;
+            for (int i = 0; i < P0; ++i)
+                if (i / a.ncomp0 == rj) pref.push_back(i);
+            for (int i = 0; i < P0; ++i)
+                if (i / a.ncomp0 != rj) pref.push_back(i);
+            std::vector<RBox> rest = D;
+            for (int i : pref) {
+                if (rest.empty()) break;
+                for (const auto &sb : S[i]) {
+                    std::vector<RBox> next;
+                    for (const auto &db : rest) {
+                        Coor u, len;
+                        if (!intersect(sb, db, u, len)) {
+                            next.push_back(db);
+                            continue;
+                        }
+                        emit(i, j, sb, db, u, len, dstr);
+                        auto left = subtract(db, sb, dst_to_range);
+                        next.insert(next.end(), left.begin(), left.end());
+                    }
+                    rest.swap(next);
+                }
+            }
+            for (const auto &db : rest) emit_zero(j, db, dstr);
+        }
+
+        plan->send_elems = wire_out;
+        plan->recv_elems = wire_in;
+        for (int r = 0; r < a.nranks; ++r)
+            if (wire_out[r] > 0 || wire_in[r] > 0) plan->needs_comm = true;
+        return plan;
+    }
+
+    std::string CopyPlan::describe() const {
+        std::stringstream ss;
+        ss << "plan rank " << rank << " of " << nranks << "\n";
+        for (int r = 0; r < nranks; ++r)
+            if (send_elems[r] || recv_elems[r])
+                ss << "wire peer " << r << " send " << send_elems[r] << " recv " << recv_elems[r]
+                   << "\n";
+        static const char *names[] = {"local", "pack", "unpack", "zero"};
+        for (const auto &op : ops) {
+            ss << "op " << names[op.kind] << " src " << op.src_part << " dst " << op.dst_part
+               << " peer " << op.peer << " soff " << op.soff << " doff " << op.doff << " size";
+            for (int s : op.size) ss << " " << s;
+            ss << " sstride";
+            for (auto s : op.sstride) ss << " " << s;
+            ss << " dstride";
+            for (auto s : op.dstride) ss << " " << s;
+            ss << "\n";
+        }
+        return ss.str();
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Plan cache (reference: cache keyed by the call geometry, dist.h:2305-2349)
+    // ---------------------------------------------------------------------------------------------
+
+    namespace {
+        std::string key_of(const CopyArgs &a) {
+            std::string k;
+            auto put = [&](const void *p, size_t n) { k.append((const char *)p, n); };
+            auto puti = [&](int v) { put(&v, sizeof v); };
+            auto putc = [&](const Coor &c) {
+                puti((int)c.size());
+                if (!c.empty()) put(c.data(), c.size() * sizeof(int));
+            };
+            puti(a.nd0), puti(a.nd1), puti(a.ncomp0), puti(a.ncomp1), puti(a.nranks), puti(a.rank);
+            puti(a.co), puti(a.add), puti(a.alpha_is_zero), puti(a.wire_align);
+            k += a.o0, k += '|', k += a.o1, k += '|';
+            putc(a.from0), putc(a.size0), putc(a.dim0), putc(a.from1), putc(a.dim1);
+            for (const auto &b : a.p0) putc(b.from), putc(b.size);
+            for (const auto &b : a.p1) putc(b.from), putc(b.size);
+            return k;
+        }
+        std::mutex cache_mutex;
+        std::map<std::string, std::shared_ptr<const CopyPlan>> &cache() {
+            static std::map<std::string, std::shared_ptr<const CopyPlan>> c;
+            return c;
+        }
+    }
+
+    std::shared_ptr<const CopyPlan> get_copy_plan(const CopyArgs &a) {
+        const std::string k = key_of(a);
+        {
+            std::lock_guard<std::mutex> g(cache_mutex);
+            auto it = cache().find(k);
+            if (it != cache().end()) return it->second;
+        }
+        auto p = make_copy_plan(a);
+        std::lock_guard<std::mutex> g(cache_mutex);
+        if (cache().size() > 4096) cache().clear();
+        cache()[k] = p;
+        return p;
+    }
+
+    void clear_plan_cache() {
+        std::lock_guard<std::mutex> g(cache_mutex);
+        cache().clear();
+    }
+
+} // namespace sbb

@@ -1,0 +1,501 @@
+// Host runtime. See runtime.hpp.
+#include "runtime.hpp"
+#include <atomic>
+#include <cstring>
+#include <dlfcn.h>
+#include <map>
+#include <mutex>
+#include <set>
+
+namespace sbb {
+
+    // ---------------------------------------------------------------------------------------------
+    // Devices, streams, launch counter
+    // ---------------------------------------------------------------------------------------------
+
+    static std::atomic<long long> g_launches{0};
+    void count_launch() { ++g_launches; }
+    long long launch_count(bool reset) {
+        long long v = g_launches.load();
+        if (reset) g_launches = 0;
+        return v;
+    }
+
+    int dtype_bytes(int dt) {
+        switch (dt) {
+        case SBB_F32: return 4;
+        case SBB_F64: return 8;
+        case SBB_C64: return 8;
+        case SBB_C128: return 16;
+        case SBB_I32: return 4;
+        default: throw std::runtime_error("unsupported element type");
+        }
+    }
+
+    namespace {
+        constexpr int MAX_DEVICES = 64;
+        DeviceState g_dev[MAX_DEVICES];
+        bool g_peer[MAX_DEVICES][MAX_DEVICES];
+        std::mutex g_mutex;
+    }
+
+    void use_device(int device) { cuda_check(cudaSetDevice(device), "cudaSetDevice"); }
+
+    DeviceState &device_state(int device) {
+        if (device < 0 || device >= MAX_DEVICES) throw std::runtime_error("invalid device id");
+        DeviceState &d = g_dev[device];
+        if (d.stream == nullptr) {
+            int count = 0;
+            cuda_check(cudaGetDeviceCount(&count), "cudaGetDeviceCount");
+            if (device >= count)
+                throw std::runtime_error("superbblas_b200: no such CUDA device (this build has no "
+                                         "CPU compute path; a B200 is required)");
+            use_device(device);
+            d.id = device;
+            cuda_check(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "stream");
+            cuda_check(cudaStreamCreateWithFlags(&d.comm_stream, cudaStreamNonBlocking), "stream");
+            cuda_check(cudaEventCreateWithFlags(&d.ev_a, cudaEventDisableTiming), "event");
+            cuda_check(cudaEventCreateWithFlags(&d.ev_b, cudaEventDisableTiming), "event");
+        }
+        return d;
+    }
+
+    void enable_peer(int a, int b) {
+        if (a == b || g_peer[a][b]) return;
+        int can = 0;
+        cuda_check(cudaDeviceCanAccessPeer(&can, a, b), "cudaDeviceCanAccessPeer");
+        if (!can) throw std::runtime_error("devices cannot access each other's memory (no NVLink/P2P)");
+        use_device(a);
+        cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled)
+            cudaGetLastError();
+        else
+            cuda_check(e, "cudaDeviceEnablePeerAccess");
+        g_peer[a][b] = true;
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Workspace pool
+    // ---------------------------------------------------------------------------------------------
+
+    namespace {
+        struct Pool {
+            std::multimap<size_t, void *> free_blocks;
+            std::map<void *, size_t> live;
+        };
+        Pool g_pool[MAX_DEVICES];
+    }
+
+    void *pool_alloc(int device, size_t bytes) {
+        if (bytes == 0) bytes = 256;
+        bytes = (bytes + 255) / 256 * 256;
+        Pool &p = g_pool[device];
+        auto it = p.free_blocks.lower_bound(bytes);
+        if (it != p.free_blocks.end() && it->first <= bytes * 2) {
+            void *ptr = it->second;
+            p.live[ptr] = it->first;
+            p.free_blocks.erase(it);
+            return ptr;
+        }
+        use_device(device);
+        void *ptr = nullptr;
+        cudaError_t e = cudaMalloc(&ptr, bytes);
+        if (e != cudaSuccess) { // release the cache and retry once (alloc.h:104-168)
+            cudaGetLastError();
+            for (auto &b : p.free_blocks) cudaFree(b.second);
+            p.free_blocks.clear();
+            cuda_check(cudaMalloc(&ptr, bytes), "cudaMalloc (workspace)");
+        }
+        p.live[ptr] = bytes;
+        return ptr;
+    }
+
+    void pool_free(int device, void *ptr) {
+        if (!ptr) return;
+        Pool &p = g_pool[device];
+        auto it = p.live.find(ptr);
+        if (it == p.live.end()) return;
+        p.free_blocks.emplace(it->second, ptr);
+        p.live.erase(it);
+    }
+
+    void pool_clear() {
+        for (int d = 0; d < MAX_DEVICES; ++d) {
+            Pool &p = g_pool[d];
+            if (p.free_blocks.empty()) continue;
+            use_device(d);
+            cudaStreamSynchronize(g_dev[d].stream);
+            for (auto &b : p.free_blocks) cudaFree(b.second);
+            p.free_blocks.clear();
+        }
+    }
+
+    void destroy_all_streams() {
+        for (int d = 0; d < MAX_DEVICES; ++d) {
+            DeviceState &s = g_dev[d];
+            if (!s.stream) continue;
+            use_device(d);
+            cudaStreamSynchronize(s.stream);
+            cudaStreamSynchronize(s.comm_stream);
+            cudaStreamDestroy(s.stream);
+            cudaStreamDestroy(s.comm_stream);
+            cudaEventDestroy(s.ev_a);
+            cudaEventDestroy(s.ev_b);
+            s = DeviceState{};
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // NCCL, loaded at run time so that the library itself has no link-time dependency on it
+    // ---------------------------------------------------------------------------------------------
+
+    namespace {
+        struct Id128 { // ncclUniqueId
+            char bytes[128];
+        };
+        struct NcclApi {
+            void *handle = nullptr;
+            int (*GetUniqueId)(void *) = nullptr;
+            int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+            int (*CommDestroy)(void *) = nullptr;
+            int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+            int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+            int (*GroupStart)() = nullptr;
+            int (*GroupEnd)() = nullptr;
+            const char *(*GetErrorString)(int) = nullptr;
+        };
+    }
+    namespace {
+        NcclApi &nccl() {
+            static NcclApi api;
+            if (api.handle) return api;
+            const char *names[] = {"libnccl.so.2", "libnccl.so"};
+            for (const char *n : names) {
+                api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+                if (api.handle) break;
+            }
+            if (!api.handle)
+                throw std::runtime_error("cannot load libnccl.so.2 (needed for multi-GPU copies)");
+            auto sym = [&](const char *name) {
+                void *p = dlsym(api.handle, name);
+                if (!p) throw std::runtime_error(std::string("NCCL symbol missing: ") + name);
+                return p;
+            };
+            api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+            api.Send = (decltype(api.Send))sym("ncclSend");
+            api.Recv = (decltype(api.Recv))sym("ncclRecv");
+            api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+            api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+            return api;
+        }
+        void nccl_check(int r, const char *what) {
+            if (r != 0)
+                throw std::runtime_error(std::string("NCCL error in ") + what + ": " +
+                                         nccl().GetErrorString(r));
+        }
+        constexpr int kNcclChar = 0; // ncclInt8 / ncclChar
+    }
+
+    void nccl_unique_id(void *id128) { nccl_check(nccl().GetUniqueId(id128), "ncclGetUniqueId"); }
+
+    Comm *comm_create(const void *id128, int nranks, int rank, int device) {
+        if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("invalid rank");
+        device_state(device);
+        use_device(device);
+        Comm *c = new Comm;
+        c->nranks = nranks, c->rank = rank, c->device = device;
+        if (nranks > 1) {
+            Id128 id;
+            std::memcpy(id.bytes, id128, 128);
+            nccl_check(nccl().CommInitRank(&c->nccl, nranks, id, rank), "ncclCommInitRank");
+        }
+        return c;
+    }
+
+    void comm_destroy(Comm *c) {
+        if (!c) return;
+        if (c->nccl) nccl().CommDestroy(c->nccl);
+        delete c;
+    }
+
+    int default_device(Comm *comm) {
+        if (comm) return comm->device;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return dev;
+    }
+
+    void order_streams(const std::set<int> &devs) {
+        if (devs.size() < 2) return;
+        for (int a : devs) {
+            DeviceState &da = device_state(a);
+            use_device(a);
+            cuda_check(cudaEventRecord(da.ev_a, da.stream), "cudaEventRecord");
+        }
+        for (int a : devs)
+            for (int b : devs) {
+                if (a == b) continue;
+                use_device(a);
+                cuda_check(cudaStreamWaitEvent(device_state(a).stream, device_state(b).ev_a, 0),
+                           "cudaStreamWaitEvent");
+            }
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // Copy executor
+    // ---------------------------------------------------------------------------------------------
+
+    namespace {
+        sbk_box_desc to_desc(const BoxOp &op) {
+            sbk_box_desc d;
+            std::memset(&d, 0, sizeof d);
+            if (op.size.size() > SBK_MAX_DIMS) throw std::runtime_error("too many dimensions");
+            d.nd = (int)op.size.size();
+            for (int k = 0; k < d.nd; ++k) {
+                d.size[k] = op.size[k];
+                d.sstride[k] = op.sstride[k];
+                d.dstride[k] = op.dstride[k];
+            }
+            return d;
+        }
+
+        struct Resolved {
+            char *ptr = nullptr;
+            int device = 0;
+            void *staged = nullptr; ///< pool block when the caller's buffer is host memory
+            void *host = nullptr;
+            size_t bytes = 0;
+            bool used = false;
+        };
+    }
+
+    void execute_copy(const CopyPlan &plan, const CopyArgs &args, int dtype0, int dtype1,
+                      const double *alpha, const std::vector<Buffer> &v0,
+                      const std::vector<Buffer> &v1, Comm *comm) {
+        if (plan.ops.empty()) return;
+        const int es0 = dtype_bytes(dtype0), es1 = dtype_bytes(dtype1);
+        // Element type on the wire: the destination type, so that conversions happen once, before
+        // sending (as the reference does, dist.h:1450-1451) -- except when adding with a type
+        // change, where the scaled source type travels so that the receiver performs exactly the
+        // arithmetic of a local `w += alpha*v` (copy_n.h:216-232)
+        const int wire_dtype = (args.add && dtype0 != dtype1) ? dtype0 : dtype1;
+        const int esw = dtype_bytes(wire_dtype);
+        const int me = plan.rank;
+        if (plan.needs_comm && (!comm || !comm->nccl))
+            throw std::runtime_error("copy needs communication but no communicator was given");
+
+        // Which components take part, and how much of every destination is overwritten
+        std::vector<Resolved> s(v0.size()), d(v1.size());
+        std::vector<int64_t> written(v1.size(), 0);
+        for (const auto &op : plan.ops) {
+            if (op.src_comp >= 0) s[op.src_comp].used = true;
+            if (op.dst_comp >= 0) d[op.dst_comp].used = true, written[op.dst_comp] += op.volume();
+        }
+
+        // Home device: where host buffers are staged and where messages are packed
+        int home = -1;
+        if (comm) home = comm->device;
+        for (size_t c = 0; c < v1.size() && home < 0; ++c)
+            if (d[c].used && !v1[c].host) home = v1[c].device;
+        for (size_t c = 0; c < v0.size() && home < 0; ++c)
+            if (s[c].used && !v0[c].host) home = v0[c].device;
+        if (home < 0) home = default_device(comm);
+        DeviceState &hs = device_state(home);
+
+        std::set<int> devs;
+        devs.insert(home);
+        for (size_t c = 0; c < v0.size(); ++c) {
+            if (!s[c].used) continue;
+            const int64_t vol = volume(args.p0[me * args.ncomp0 + c].size);
+            s[c].bytes = (size_t)vol * es0;
+            if (v0[c].ptr == nullptr) throw std::runtime_error("null pointer for a non-empty component");
+            if (v0[c].host) {
+                s[c].host = v0[c].ptr;
+                s[c].device = home;
+                s[c].staged = pool_alloc(home, s[c].bytes);
+                s[c].ptr = (char *)s[c].staged;
+                use_device(home);
+                cuda_check(cudaMemcpyAsync(s[c].ptr, v0[c].ptr, s[c].bytes, cudaMemcpyHostToDevice,
+                                           hs.stream),
+                           "cudaMemcpyAsync H2D");
+            } else {
+                s[c].ptr = (char *)v0[c].ptr, s[c].device = v0[c].device;
+                device_state(s[c].device);
+            }
+            devs.insert(s[c].device);
+        }
+        for (size_t c = 0; c < v1.size(); ++c) {
+            if (!d[c].used) continue;
+            const int64_t vol = volume(args.p1[me * args.ncomp1 + c].size);
+            d[c].bytes = (size_t)vol * es1;
+            if (v1[c].ptr == nullptr) throw std::runtime_error("null pointer for a non-empty component");
+            if (v1[c].host) {
+                d[c].host = v1[c].ptr;
+                d[c].device = home;
+                d[c].staged = pool_alloc(home, d[c].bytes);
+                d[c].ptr = (char *)d[c].staged;
+                // keep what the copy does not overwrite (Copy ops never overlap, see plan.cpp)
+                if (args.add || written[c] < vol) {
+                    use_device(home);
+                    cuda_check(cudaMemcpyAsync(d[c].ptr, v1[c].ptr, d[c].bytes,
+                                               cudaMemcpyHostToDevice, hs.stream),
+                               "cudaMemcpyAsync H2D");
+                }
+            } else {
+                d[c].ptr = (char *)v1[c].ptr, d[c].device = v1[c].device;
+                device_state(d[c].device);
+            }
+            devs.insert(d[c].device);
+        }
+
+        // Several devices in one process: order their streams before and after (the reference's
+        // causalConnectTo, platform.h:371-409)
+        auto cross_sync = [&](bool begin) {
+            if (devs.size() < 2) return;
+            for (int a : devs) {
+                DeviceState &da = device_state(a);
+                use_device(a);
+                cuda_check(cudaEventRecord(begin ? da.ev_a : da.ev_b, da.stream), "cudaEventRecord");
+            }
+            for (int a : devs)
+                for (int b : devs) {
+                    if (a == b) continue;
+                    use_device(a);
+                    cuda_check(cudaStreamWaitEvent(device_state(a).stream,
+                                                   begin ? device_state(b).ev_a : device_state(b).ev_b, 0),
+                               "cudaStreamWaitEvent");
+                }
+        };
+        cross_sync(true);
+
+        // Message buffers: one 256-byte aligned segment per peer
+        std::vector<size_t> seg_send(plan.nranks + 1, 0), seg_recv(plan.nranks + 1, 0);
+        char *sendbuf = nullptr, *recvbuf = nullptr;
+        if (plan.needs_comm) {
+            for (int r = 0; r < plan.nranks; ++r) {
+                seg_send[r + 1] = seg_send[r] + ((size_t)plan.send_elems[r] * esw + 255) / 256 * 256;
+                seg_recv[r + 1] = seg_recv[r] + ((size_t)plan.recv_elems[r] * esw + 255) / 256 * 256;
+            }
+            if (seg_send[plan.nranks]) sendbuf = (char *)pool_alloc(home, seg_send[plan.nranks]);
+            if (seg_recv[plan.nranks]) recvbuf = (char *)pool_alloc(home, seg_recv[plan.nranks]);
+        }
+
+        const double one[2] = {1, 0}, zero[2] = {0, 0};
+        auto run = [&](const BoxOp &op) {
+            sbk_box_desc desc = to_desc(op);
+            switch (op.kind) {
+            case BoxOp::Local: {
+                const Resolved &a = s[op.src_comp], &b = d[op.dst_comp];
+                enable_peer(b.device, a.device);
+                use_device(b.device);
+                desc.soff = op.soff, desc.doff = op.doff;
+                permute_copy(desc, a.ptr, dtype0, b.ptr, dtype1, alpha, args.add, b.device,
+                             device_state(b.device).stream);
+                break;
+            }
+            case BoxOp::Pack: {
+                const Resolved &a = s[op.src_comp];
+                enable_peer(home, a.device);
+                use_device(home);
+                desc.soff = op.soff, desc.doff = op.doff;
+                // scaled (and normally converted) before it leaves
+                permute_copy(desc, a.ptr, dtype0, sendbuf + seg_send[op.peer], wire_dtype, alpha,
+                             false, home, hs.stream);
+                break;
+            }
+            case BoxOp::Unpack: {
+                const Resolved &b = d[op.dst_comp];
+                enable_peer(b.device, home);
+                use_device(b.device);
+                desc.soff = op.soff, desc.doff = op.doff;
+                permute_copy(desc, recvbuf + seg_recv[op.peer], wire_dtype, b.ptr, dtype1, one,
+                             args.add, b.device, device_state(b.device).stream);
+                break;
+            }
+            case BoxOp::Zero: {
+                const Resolved &b = d[op.dst_comp];
+                use_device(b.device);
+                desc.doff = op.doff;
+                permute_copy(desc, nullptr, dtype1, b.ptr, dtype1, zero, false, b.device,
+                             device_state(b.device).stream);
+                break;
+            }
+            }
+        };
+
+        auto exchange = [&]() {
+            // pack kernels (home stream) -> NCCL (comm stream)
+            use_device(home);
+            cuda_check(cudaEventRecord(hs.ev_a, hs.stream), "cudaEventRecord");
+            cuda_check(cudaStreamWaitEvent(hs.comm_stream, hs.ev_a, 0), "cudaStreamWaitEvent");
+            NcclApi &n = nccl();
+            nccl_check(n.GroupStart(), "ncclGroupStart");
+            for (int r = 0; r < plan.nranks; ++r) {
+                if (plan.send_elems[r] > 0)
+                    nccl_check(n.Send(sendbuf + seg_send[r], (size_t)plan.send_elems[r] * esw,
+                                      kNcclChar, r, comm->nccl, hs.comm_stream),
+                               "ncclSend");
+                if (plan.recv_elems[r] > 0)
+                    nccl_check(n.Recv(recvbuf + seg_recv[r], (size_t)plan.recv_elems[r] * esw,
+                                      kNcclChar, r, comm->nccl, hs.comm_stream),
+                               "ncclRecv");
+            }
+            nccl_check(n.GroupEnd(), "ncclGroupEnd");
+            cuda_check(cudaEventRecord(hs.ev_b, hs.comm_stream), "cudaEventRecord");
+        };
+        auto wait_exchange = [&]() {
+            for (int a : devs) {
+                use_device(a);
+                cuda_check(cudaStreamWaitEvent(device_state(a).stream, hs.ev_b, 0),
+                           "cudaStreamWaitEvent");
+            }
+        };
+
+        if (plan.needs_comm) {
+            for (const auto &op : plan.ops)
+                if (op.kind == BoxOp::Pack) run(op);
+            exchange();
+            if (args.add) {
+                // additions are applied in plan order (ascending source part) so that the result
+                // does not depend on which contributions were remote
+                wait_exchange();
+                for (const auto &op : plan.ops)
+                    if (op.kind != BoxOp::Pack) run(op);
+            } else {
+                // local part overlaps the transfer
+                for (const auto &op : plan.ops)
+                    if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
+                wait_exchange();
+                for (const auto &op : plan.ops)
+                    if (op.kind == BoxOp::Unpack) run(op);
+            }
+        } else {
+            for (const auto &op : plan.ops) run(op);
+        }
+
+        cross_sync(false);
+
+        // Host destinations are complete when the call returns
+        bool host_out = false;
+        for (size_t c = 0; c < v1.size(); ++c)
+            if (d[c].used && d[c].host) {
+                use_device(home);
+                cuda_check(cudaMemcpyAsync(d[c].host, d[c].ptr, d[c].bytes, cudaMemcpyDeviceToHost,
+                                           hs.stream),
+                           "cudaMemcpyAsync D2H");
+                host_out = true;
+            }
+        if (host_out) {
+            use_device(home);
+            cuda_check(cudaStreamSynchronize(hs.stream), "cudaStreamSynchronize");
+        }
+        for (auto &r : s) pool_free(home, r.staged);
+        for (auto &r : d) pool_free(home, r.staged);
+        pool_free(home, sendbuf);
+        pool_free(home, recvbuf);
+    }
+
+} // namespace sbb

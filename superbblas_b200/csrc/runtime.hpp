@@ -1,0 +1,58 @@
+// Host runtime: per-device streams, workspace pool, NCCL communicator, and the executors that turn
+// a plan into kernel launches.
+//
+// Reference counterparts: one persistent stream per device (platform.h:456-467), buffer pool
+// (alloc.h:323-391), causalConnectTo (platform.h:371-409), send_receive (dist.h:1426-1573).
+#pragma once
+#include "kernels.hpp"
+#include "plan.hpp"
+#include <set>
+#include <vector>
+
+namespace sbb {
+
+    struct DeviceState {
+        int id = -1;
+        cudaStream_t stream = nullptr;      ///< all kernels of the library for this device
+        cudaStream_t comm_stream = nullptr; ///< NCCL traffic, overlapped with `stream`
+        cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    };
+
+    DeviceState &device_state(int device);
+    void use_device(int device);
+    void enable_peer(int a, int b);
+    void destroy_all_streams();
+    /// Make every listed device's stream wait for the work already queued on the others
+    void order_streams(const std::set<int> &devs);
+
+    /// Cached device allocations (reused by later calls on the same stream)
+    void *pool_alloc(int device, size_t bytes);
+    void pool_free(int device, void *p);
+    void pool_clear();
+
+    struct Comm {
+        void *nccl = nullptr; ///< ncclComm_t
+        int nranks = 1, rank = 0, device = 0;
+    };
+
+    void nccl_unique_id(void *id128);
+    Comm *comm_create(const void *id128, int nranks, int rank, int device);
+    void comm_destroy(Comm *c);
+
+    /// A component buffer as given by the caller
+    struct Buffer {
+        void *ptr = nullptr;
+        bool host = false;
+        int device = 0;
+    };
+
+    void execute_copy(const CopyPlan &plan, const CopyArgs &args, int dtype0, int dtype1,
+                      const double *alpha, const std::vector<Buffer> &v0,
+                      const std::vector<Buffer> &v1, Comm *comm);
+
+    long long launch_count(bool reset);
+
+    /// Default device for staging host buffers when no GPU component takes part
+    int default_device(Comm *comm);
+
+} // namespace sbb

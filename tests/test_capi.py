@@ -1,0 +1,90 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/superbblas_b200.h
+declares; host-only entry points (partitions, make_hole) agree with the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+
+import superbblas_b200 as sb
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "superbblas_b200.h")).read()
+    names = set(re.findall(r"\b(sb[bk]_[a-z_0-9]+)\s*\(", header))
+    assert len(names) >= 20
+    lib = ctypes.CDLL(sb.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+    assert b"sm_100a" in ctypes.cast(lib.sbb_version, ctypes.CFUNCTYPE(ctypes.c_char_p))()
+
+
+def test_context_layout_matches_reference():
+    # class Context {enum platform plat; int device;} (platform.h:757-765)
+    assert ctypes.sizeof(sb.Context) == 8
+    assert sb.Context.plat.offset == 0 and sb.Context.device.offset == 4
+    assert sb.createGpuContext(3).plat == 1 and sb.createGpuContext(3).device == 3
+    assert sb.createCpuContext().plat == 0
+
+
+def test_partitions_match_oracle():
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        n = int(rng.integers(1, 7))
+        order = "".join(rng.permutation(list("xyztscn"))[:n])
+        dim = [int(rng.integers(1, 13)) for _ in range(n)]
+        labels = "".join(rng.permutation(list(order))[:int(rng.integers(1, n + 1))])
+        nprocs = int(rng.integers(1, 25))
+        procs = sb.partitioning_distributed_procs(order, dim, labels, nprocs)
+        assert procs == O.partitioning_distributed_procs(order, dim, labels, nprocs)
+        ncomp = int(rng.integers(1, 4))
+        P = int(np.prod(procs))
+        assert np.array_equal(sb.basic_partitioning(order, dim, procs, labels, P, ncomp),
+                              O.basic_partitioning(order, dim, procs, labels, P, ncomp))
+        ext = [int(rng.integers(0, 3)) for _ in range(n)]
+        assert np.array_equal(sb.basic_partitioning(dim, procs, P, False, ext),
+                              O.basic_partitioning_ext(dim, procs, P, False, ext))
+
+
+def test_known_partition_answers():
+    # tests/dist.cpp:103-125 of the reference
+    assert sb.partitioning_distributed_procs("xyzt", [8, 8, 8, 16], "zt", 8) == [1, 1, 2, 4]
+    p = sb.basic_partitioning("xyztscn", [32, 32, 32, 64, 4, 3, 128], [1, 1, 2, 4, 1, 1, 1], "zt", 8)
+    # rank = 4*jz + jt
+    for jz in range(2):
+        for jt in range(4):
+            assert list(p[4 * jz + jt, 0]) == [0, 0, 16 * jz, 16 * jt, 0, 0, 0]
+            assert list(p[4 * jz + jt, 1]) == [32, 32, 16, 16, 4, 3, 128]
+
+
+def test_make_hole_matches_oracle_sets():
+    rng = np.random.default_rng(6)
+    for _ in range(200):
+        n = int(rng.integers(1, 4))
+        dim = [int(rng.integers(1, 7)) for _ in range(n)]
+        frm = [int(rng.integers(0, d)) for d in dim]
+        size = [int(rng.integers(1, d + 1)) for d in dim]
+        hf = [int(rng.integers(0, d)) for d in dim]
+        hs = [int(rng.integers(0, d + 1)) for d in dim]
+        boxes = sb.make_hole(frm, size, hf, hs, dim)
+        a = O.box_elements(boxes, dim)
+        b = O.box_elements(O.make_hole(frm, size, hf, hs, dim), dim)
+        assert np.array_equal(a, b)
+        assert len(np.unique(a)) == len(a)  # boxes do not overlap
+
+
+def test_no_cuda_device_fails_loudly():
+    if sb.getGpuDevicesCount() > 0:
+        return
+    p = np.array([[[0], [4]]], dtype=np.int32)
+    x, y = np.zeros(4), np.zeros(4)
+    try:
+        sb.copy(1, p, 1, "x", [0], [4], [4], [x], None, sb.createCpuContext(), p, 1, "x", [0], [4],
+                [y], None, sb.createCpuContext(), sb.FastToSlow, sb.Copy)
+    except RuntimeError as e:
+        assert "CUDA" in str(e) or "device" in str(e)
+    else:
+        raise AssertionError("copy must not succeed without a GPU (no CPU compute path)")
