@@ -63,6 +63,12 @@ int sbb_get_stream(int device, void **stream);
 /* Number of CUDA kernels launched by the library since the last call with reset != 0 */
 int sbb_launch_count(int reset, long long *count);
 
+/* Device-side timing of the library's own kernels: when enabled every launch of the copy kernel
+ * ("permute") and of the tensor-core contraction kernel ("contract_mma") is bracketed by CUDA events
+ * on its stream; sbb_profile_read synchronises, returns the summed duration and clears the list. */
+int sbb_profile_enable(int on);
+int sbb_profile_read(const char *kernel, double *total_ms, long long *count);
+
 /* ---- communicator (NCCL over NVLink) ------------------------------------------------------------ */
 
 /* Write a 128-byte NCCL unique id (rank 0 calls it and broadcasts the bytes by any means) */

@@ -76,6 +76,17 @@ def launch_count(reset=False):
     return n.value
 
 
+def profile_enable(on=True):
+    check(lib().sbb_profile_enable(int(on)))
+
+
+def profile_read(kernel):
+    """-> (total milliseconds, launches) of the named kernel since the last read"""
+    ms, n = ctypes.c_double(0), ctypes.c_longlong(0)
+    check(lib().sbb_profile_read(kernel.encode(), ctypes.byref(ms), ctypes.byref(n)))
+    return ms.value, n.value
+
+
 # --- communicator -------------------------------------------------------------------------------
 
 class Comm:

@@ -131,6 +131,12 @@ int sbb_get_stream(int device, void **stream) { SBB_TRY(*stream = device_state(d
 
 int sbb_launch_count(int reset, long long *count) { SBB_TRY(*count = launch_count(reset != 0)); }
 
+int sbb_profile_enable(int on) { SBB_TRY(profile_enable(on != 0)); }
+
+int sbb_profile_read(const char *kernel, double *total_ms, long long *count) {
+    SBB_TRY(profile_read(kernel, total_ms, count));
+}
+
 int sbb_comm_unique_id(void *id128) { SBB_TRY(nccl_unique_id(id128)); }
 
 int sbb_comm_create(const void *id128, int nranks, int rank, int device, sbb_comm_t *comm) {

@@ -18,6 +18,20 @@ namespace sbb {
 
     int dtype_bytes(int dtype);
 
+    /// Optional device-side timing of the library's own kernels (bench.py's roofline numbers):
+    /// when enabled, a pair of CUDA events brackets every launch of the named kernel on the stream
+    /// it is launched on.
+    struct KernelTimer {
+        KernelTimer(const char *name, cudaStream_t stream);
+        ~KernelTimer();
+        const char *name;
+        cudaStream_t stream;
+        bool on;
+    };
+    void profile_enable(bool on);
+    /// Synchronise, sum and clear the recorded launches of `name`
+    void profile_read(const char *name, double *total_ms, long long *count);
+
     /// dst (+)= Q(alpha*src) over a strided box. The current device must be `device`.
     /// If `describe` is given nothing is launched and the chosen variant is described instead.
     void permute_copy(const sbk_box_desc &box, const void *src, int dtype_src, void *dst,

@@ -507,8 +507,11 @@ namespace sbb {
                            "cudaFuncSetAttribute");
                 attr_set[device] = true;
             }
-            contract_mma_kernel<T><<<(unsigned)ctas, MMA_THREADS, smem, stream>>>(p, (const T *)v0,
-                                                                                 (const T *)v1, ws);
+            {
+                KernelTimer timer("contract_mma", stream);
+                contract_mma_kernel<T><<<(unsigned)ctas, MMA_THREADS, smem, stream>>>(
+                    p, (const T *)v0, (const T *)v1, ws);
+            }
             count_launch();
             cuda_check(cudaGetLastError(), "contract_mma_kernel launch");
             const long long total = p.T.vol * p.M.vol * p.N.vol;

@@ -229,7 +229,14 @@ namespace sbb {
                 }
             }
 
-            // ---- tile loop ----------------------------------------------------------------------
+            // ---- tile loop, software pipelined -----------------------------------------------------
+            // The loads of the next tile are in flight while the current tile is being stored, so a
+            // CTA always has a tile's worth of bytes outstanding (HBM latency x bandwidth needs
+            // ~40 KB per SM in flight).
+            struct Tile {
+                long long sbase, dbase;
+                unsigned mask_l, mask_s; // slots to load / to store (all live slots on full tiles)
+            };
             unsigned tc[KD];
             {
                 unsigned t = blockIdx.x;
@@ -242,65 +249,20 @@ namespace sbb {
                     }
                 }
             }
-            for (unsigned tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-                long long sbase = 0, dbase = 0;
+            auto tile_info = [&]() {
+                Tile t;
+                t.sbase = 0, t.dbase = 0;
                 bool full = true;
 #pragma unroll
                 for (int d = 0; d < KD; ++d)
                     if (d < p.nd) {
-                        sbase += tc[d] * p.tsstride[d];
-                        dbase += tc[d] * p.tdstride[d];
+                        t.sbase += tc[d] * p.tsstride[d];
+                        t.dbase += tc[d] * p.tdstride[d];
                         full = full && ((tc[d] + 1) * (unsigned)p.te[d] <= (unsigned)p.size[d]);
                     }
-                const T *s = src + sbase;
-                Q *w = dst + dbase;
-
-                if (full) {
-                    if (SMEM) {
-                        T r[EPT];
-#pragma unroll
-                        for (int k = 0; k < EPT; ++k)
-                            if (live >> k & 1) r[k] = s[so[k]];
-#pragma unroll
-                        for (int k = 0; k < EPT; ++k)
-                            if (live >> k & 1) smem[sp[k] >> 16] = r[k];
-                        __syncthreads();
-                        if (op.add()) {
-                            Q o[EPT];
-#pragma unroll
-                            for (int k = 0; k < EPT; ++k)
-                                if (live >> k & 1) o[k] = w[dof[k]];
-#pragma unroll
-                            for (int k = 0; k < EPT; ++k)
-                                if (live >> k & 1)
-                                    w[dof[k]] = op.combine(o[k], smem[sp[k] & 0xffffu]);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < EPT; ++k)
-                                if (live >> k & 1) w[dof[k]] = op.apply(smem[sp[k] & 0xffffu]);
-                        }
-                        __syncthreads();
-                    } else {
-                        T r[EPT];
-#pragma unroll
-                        for (int k = 0; k < EPT; ++k)
-                            if (live >> k & 1) r[k] = s[so[k]];
-                        if (op.add()) {
-                            Q o[EPT];
-#pragma unroll
-                            for (int k = 0; k < EPT; ++k)
-                                if (live >> k & 1) o[k] = w[dof[k]];
-#pragma unroll
-                            for (int k = 0; k < EPT; ++k)
-                                if (live >> k & 1) w[dof[k]] = op.combine(o[k], r[k]);
-                        } else {
-#pragma unroll
-                            for (int k = 0; k < EPT; ++k)
-                                if (live >> k & 1) w[dof[k]] = op.apply(r[k]);
-                        }
-                    }
-                } else {
-                    // boundary tile: recompute coordinates to mask what falls outside the box
+                t.mask_l = t.mask_s = live;
+                if (!full) {
+                    // boundary tile: mask the slots that fall outside the box
                     int lim[MAXT];
 #pragma unroll
                     for (int q = 0; q < MAXT; ++q) {
@@ -322,30 +284,18 @@ namespace sbb {
                         for (int q = 0; q < MAXT; ++q) ok = ok && (c[q] < lim[q]);
                         return ok;
                     };
-                    if (SMEM) {
+                    t.mask_l = t.mask_s = 0;
 #pragma unroll
-                        for (int k = 0; k < EPT; ++k)
-                            if ((live >> k & 1) && inside(tid + k * NT, p.sord))
-                                smem[sp[k] >> 16] = s[so[k]];
-                        __syncthreads();
-#pragma unroll
-                        for (int k = 0; k < EPT; ++k)
-                            if ((live >> k & 1) && inside(tid + k * NT, dord)) {
-                                const T x = smem[sp[k] & 0xffffu];
-                                w[dof[k]] = op.add() ? op.combine(w[dof[k]], x) : op.apply(x);
-                            }
-                        __syncthreads();
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < EPT; ++k)
-                            if ((live >> k & 1) && inside(tid + k * NT, dord)) {
-                                const T x = s[so[k]];
-                                w[dof[k]] = op.add() ? op.combine(w[dof[k]], x) : op.apply(x);
-                            }
-                    }
+                    for (int k = 0; k < EPT; ++k)
+                        if (live >> k & 1) {
+                            if (inside(tid + k * NT, dord)) t.mask_s |= 1u << k;
+                            if (SMEM && inside(tid + k * NT, p.sord)) t.mask_l |= 1u << k;
+                        }
+                    if (!SMEM) t.mask_l = t.mask_s;
                 }
-
-                // next tile of this CTA: tc += delta with carries
+                return t;
+            };
+            auto advance = [&]() { // tc += delta with carries
                 unsigned carry = 0;
 #pragma unroll
                 for (int d = 0; d < KD; ++d)
@@ -355,6 +305,68 @@ namespace sbb {
                         if (carry) v -= p.ntile[d];
                         tc[d] = v;
                     }
+            };
+            auto load = [&](const Tile &t, T(&r)[EPT]) {
+                const T *s = src + t.sbase;
+#pragma unroll
+                for (int k = 0; k < EPT; ++k)
+                    if (t.mask_l >> k & 1) r[k] = s[so[k]];
+            };
+
+            if (blockIdx.x >= p.ntiles) return;
+            const unsigned my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+            Tile cur = tile_info();
+            T r[EPT];
+            load(cur, r);
+            for (unsigned i = 0; i < my_tiles; ++i) {
+                const bool has_next = i + 1 < my_tiles;
+                Tile nxt = cur;
+                if (has_next) {
+                    advance();
+                    nxt = tile_info();
+                }
+                Q *w = dst + cur.dbase;
+                if (SMEM) {
+#pragma unroll
+                    for (int k = 0; k < EPT; ++k)
+                        if (cur.mask_l >> k & 1) smem[sp[k] >> 16] = r[k];
+                    __syncthreads();
+                    if (has_next) load(nxt, r); // in flight during the store phase
+                    if (op.add()) {
+                        Q o[EPT];
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if (cur.mask_s >> k & 1) o[k] = w[dof[k]];
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if (cur.mask_s >> k & 1)
+                                w[dof[k]] = op.combine(o[k], smem[sp[k] & 0xffffu]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if (cur.mask_s >> k & 1) w[dof[k]] = op.apply(smem[sp[k] & 0xffffu]);
+                    }
+                    __syncthreads();
+                } else {
+                    T r2[EPT];
+                    if (has_next) load(nxt, r2);
+                    if (op.add()) {
+                        Q o[EPT];
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if (cur.mask_s >> k & 1) o[k] = w[dof[k]];
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if (cur.mask_s >> k & 1) w[dof[k]] = op.combine(o[k], r[k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if (cur.mask_s >> k & 1) w[dof[k]] = op.apply(r[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < EPT; ++k) r[k] = r2[k];
+                }
+                cur = nxt;
             }
         }
 
@@ -464,11 +476,21 @@ namespace sbb {
                           int64_t want_s) {
             Tiling t;
             t.te.assign(c.nd, 1);
+            // extent close to `need` that divides the dimension when there is one (full tiles only)
+            auto pick = [](int size, int64_t need) {
+                int ext = (int)std::min<int64_t>(size, need);
+                if (size % ext == 0) return ext;
+                for (int e = ext; e <= std::min<int64_t>(size, 2 * (int64_t)ext); ++e)
+                    if (size % e == 0) return e;
+                for (int e = ext; e > ext / 2 && e >= 1; --e)
+                    if (size % e == 0) return e;
+                return ext;
+            };
             int64_t acc = 1;
             for (int d = 0; d < c.nd && acc < want_d; ++d) {
                 if (d == 0 ? false : c.ds[d] != c.ds[d - 1] * c.size[d - 1]) break;
                 const int64_t need = (want_d + acc - 1) / acc;
-                const int ext = (int)std::min<int64_t>(c.size[d], need);
+                const int ext = pick(c.size[d], need);
                 t.te[d] = ext;
                 acc *= ext;
                 if (ext < c.size[d]) break;
@@ -479,7 +501,7 @@ namespace sbb {
                 if (q > 0 && c.ss[d] != c.ss[sorder[q - 1]] * c.size[sorder[q - 1]]) break;
                 if (q > 0 && t.te[sorder[q - 1]] < c.size[sorder[q - 1]]) break;
                 const int64_t need = (want_s + acc - 1) / acc;
-                const int ext = std::max<int>(t.te[d], (int)std::min<int64_t>(c.size[d], need));
+                const int ext = std::max<int>(t.te[d], pick(c.size[d], need));
                 t.te[d] = ext;
                 acc *= ext;
                 if (ext < c.size[d]) break;
@@ -673,7 +695,10 @@ namespace sbb {
                 const unsigned grid = (unsigned)std::min<int64_t>(
                     lp.p.ntiles, (int64_t)dev_info(device).sms * it->second);
                 set_delta(lp.p, grid);
-                kernel<<<grid, NT, smem_bytes, stream>>>(lp.p, (const T *)src, (Q *)dst, op);
+                {
+                    KernelTimer timer("permute", stream);
+                    kernel<<<grid, NT, smem_bytes, stream>>>(lp.p, (const T *)src, (Q *)dst, op);
+                }
                 count_launch();
                 cuda_check(cudaGetLastError(), "permute_kernel launch");
             };
@@ -777,9 +802,43 @@ namespace sbb {
             if (is_zero && add) return;
             Canon c = c0;
             std::stringstream ds;
+            // Prepared launches are cached by geometry, types, flags and pointer alignment: the
+            // tiling search runs once per distinct copy (the reference caches its index vectors
+            // the same way, tensor.h:946-951 -- here the cached object is ~0.5 KB, not the index).
+            struct Prepared {
+                Canon c;
+                LaunchPlan lp;
+                int es;
+            };
+            static std::map<std::string, Prepared> cache;
+            std::string key;
+            {
+                auto put = [&](const void *ptr, size_t n) { key.append((const char *)ptr, n); };
+                const int flags[6] = {dt0, dt1, is_zero, is_one, add,
+                                      (int)(((uintptr_t)src & 15) | (((uintptr_t)dst & 15) << 4))};
+                put(flags, sizeof flags);
+                put(&c0.nd, sizeof c0.nd);
+                put(c0.size.data(), c0.size.size() * sizeof(int));
+                put(c0.ss.data(), c0.ss.size() * sizeof(int64_t));
+                put(c0.ds.data(), c0.ds.size() * sizeof(int64_t));
+                put(&c0.soff, sizeof c0.soff);
+                put(&c0.doff, sizeof c0.doff);
+            }
+            auto hit = describe ? cache.end() : cache.find(key);
+            auto remember = [&](const Canon &cc, const LaunchPlan &lp, int es) {
+                if (cache.size() > 8192) cache.clear();
+                cache[key] = Prepared{cc, lp, es};
+            };
             if (is_zero) {
-                int es = promote(c, dtype_size(dt1), nullptr, dst, false);
-                LaunchPlan lp = plan_launch(c, es, NT * EPT, false);
+                int es;
+                LaunchPlan lp;
+                if (hit != cache.end()) {
+                    c = hit->second.c, lp = hit->second.lp, es = hit->second.es;
+                } else {
+                    es = promote(c, dtype_size(dt1), nullptr, dst, false);
+                    lp = plan_launch(c, es, NT * EPT, false);
+                    if (!describe) remember(c, lp, es);
+                }
                 if (describe) {
                     ds << "zero es=" << es << " tile=" << lp.p.tile_elems << " ntiles=" << lp.p.ntiles;
                     *describe = ds.str();
@@ -792,8 +851,15 @@ namespace sbb {
                 return;
             }
             if (dt0 == dt1 && is_one && !add) {
-                int es = promote(c, dtype_size(dt0), src, dst, true);
-                LaunchPlan lp = plan_launch(c, es, max_tile_for(es), true);
+                int es;
+                LaunchPlan lp;
+                if (hit != cache.end()) {
+                    c = hit->second.c, lp = hit->second.lp, es = hit->second.es;
+                } else {
+                    es = promote(c, dtype_size(dt0), src, dst, true);
+                    lp = plan_launch(c, es, max_tile_for(es), true);
+                    if (!describe) remember(c, lp, es);
+                }
                 if (describe) {
                     ds << (lp.smem ? "move tiled" : "move direct") << " es=" << es
                        << " tile=" << lp.p.tile_elems << " ntiles=" << lp.p.ntiles
@@ -811,7 +877,13 @@ namespace sbb {
             }
             // typed path on native elements
             const int es0 = dtype_size(dt0), es1 = dtype_size(dt1);
-            LaunchPlan lp = plan_launch(c, std::max(es0, es1), NT * EPT, true);
+            LaunchPlan lp;
+            if (hit != cache.end()) {
+                lp = hit->second.lp;
+            } else {
+                lp = plan_launch(c, std::max(es0, es1), NT * EPT, true);
+                if (!describe) remember(c, lp, 0);
+            }
             if (describe) {
                 ds << (lp.smem ? "typed tiled" : "typed direct") << " es=" << es0 << "->" << es1
                    << " tile=" << lp.p.tile_elems << " ntiles=" << lp.p.ntiles

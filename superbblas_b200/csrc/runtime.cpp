@@ -6,6 +6,8 @@
 #include <map>
 #include <mutex>
 #include <set>
+#include <string>
+#include <vector>
 
 namespace sbb {
 
@@ -19,6 +21,47 @@ namespace sbb {
         long long v = g_launches.load();
         if (reset) g_launches = 0;
         return v;
+    }
+
+    namespace {
+        bool g_profile = false;
+        struct TimedLaunch {
+            cudaEvent_t a, b;
+        };
+        std::map<std::string, std::vector<TimedLaunch>> g_timed;
+    }
+
+    void profile_enable(bool on) { g_profile = on; }
+
+    KernelTimer::KernelTimer(const char *name_, cudaStream_t stream_)
+        : name(name_), stream(stream_), on(g_profile) {
+        if (!on) return;
+        TimedLaunch t;
+        cuda_check(cudaEventCreate(&t.a), "cudaEventCreate");
+        cuda_check(cudaEventCreate(&t.b), "cudaEventCreate");
+        cuda_check(cudaEventRecord(t.a, stream), "cudaEventRecord");
+        g_timed[name].push_back(t);
+    }
+
+    KernelTimer::~KernelTimer() {
+        if (!on) return;
+        cudaEventRecord(g_timed[name].back().b, stream);
+    }
+
+    void profile_read(const char *name, double *total_ms, long long *count) {
+        *total_ms = 0, *count = 0;
+        auto it = g_timed.find(name);
+        if (it == g_timed.end()) return;
+        for (auto &t : it->second) {
+            cuda_check(cudaEventSynchronize(t.b), "cudaEventSynchronize");
+            float ms = 0;
+            cuda_check(cudaEventElapsedTime(&ms, t.a, t.b), "cudaEventElapsedTime");
+            *total_ms += ms;
+            ++*count;
+            cudaEventDestroy(t.a);
+            cudaEventDestroy(t.b);
+        }
+        it->second.clear();
     }
 
     int dtype_bytes(int dt) {

@@ -1,0 +1,34 @@
+"""N>1 path.  CPU: world_size 2 and 3 with the gloo backend (host logic: plans, message layout,
+ordering).  GPU: world_size = number of devices (>= 2) with NCCL inside the library."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def launch(n, backend, cases, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "dist_check.py"), "--backend", backend, "--cases", str(cases)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0, out[-3000:]
+    assert "failures=0" in out, out[-3000:]
+
+
+@pytest.mark.parametrize("n", [2, 3])
+def test_gloo_world(n):
+    launch(n, "gloo", 25, 29511 + n)
+
+
+@pytest.mark.gpu
+def test_nccl_world():
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    launch(min(n, 8), "nccl", 20, 29531)
