@@ -348,7 +348,10 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128",
             "data": "synthetic", "config": workload_config(world),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the
+                         # ncu --set full capture in profiles/r1_contract_mma_ncu.txt
+                         "traffic": 12.885870e9 + 140.346368e6,
                          "kernel": "contract_mma_kernel<double2>", "kernel_ms": kernel_ms,
                          "flop_per_launch": FLOP_PER_GPU,
                          "peak_source": "FP64 path: measured live, cuBLAS ZGEMM 4096^3 via "
