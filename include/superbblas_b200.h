@@ -144,6 +144,10 @@ typedef struct sbk_box_desc {
     int64_t sstride[SBK_MAX_DIMS];
     int64_t dstride[SBK_MAX_DIMS];
     int64_t soff, doff;
+    /* Periodic rotation of dimension 0: element i_0 goes to destination index (i_0 + rot) mod
+     * size[0] (0 = none).  Requires sstride[0] == dstride[0] == 1.  This is how a +-1 shift along
+     * the fastest label is done in one pass over whole rows instead of two boxes. */
+    int rot;
 } sbk_box_desc;
 
 /* dst (+)= Q(alpha*src) over the box; alpha==0 with add==0 zero-fills without reading src.

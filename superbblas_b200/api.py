@@ -302,12 +302,13 @@ def copy_plan(elem_size1, p0, ncomponents0, o0, from0, size0, dim0, p1, ncompone
         if w[0] == "wire":
             wire[int(w[2])] = (int(w[4]), int(w[6]))
         elif w[0] == "op":
-            i_size, i_ss, i_ds = w.index("size"), w.index("sstride"), w.index("dstride")
+            i_size, i_ss, i_ds, i_rot = (w.index("size"), w.index("sstride"), w.index("dstride"),
+                                         w.index("rot"))
             ops.append(dict(kind=w[1], src=int(w[3]), dst=int(w[5]), peer=int(w[7]),
                             soff=int(w[9]), doff=int(w[11]),
                             size=[int(x) for x in w[i_size + 1:i_ss]],
                             sstride=[int(x) for x in w[i_ss + 1:i_ds]],
-                            dstride=[int(x) for x in w[i_ds + 1:]]))
+                            dstride=[int(x) for x in w[i_ds + 1:i_rot]], rot=int(w[i_rot + 1])))
     return ops, wire
 
 
@@ -353,11 +354,12 @@ def local_contraction(alpha, o0, dim0, conj0, v0, o1, dim1, conj1, v1, beta, o_r
 class BoxDesc(ctypes.Structure):
     _fields_ = [("nd", ctypes.c_int), ("size", ctypes.c_int * 16),
                 ("sstride", ctypes.c_int64 * 16), ("dstride", ctypes.c_int64 * 16),
-                ("soff", ctypes.c_int64), ("doff", ctypes.c_int64)]
+                ("soff", ctypes.c_int64), ("doff", ctypes.c_int64), ("rot", ctypes.c_int)]
 
 
-def box_desc(size, sstride, dstride, soff=0, doff=0):
+def box_desc(size, sstride, dstride, soff=0, doff=0, rot=0):
     d = BoxDesc()
+    d.rot = int(rot)
     d.nd = len(size)
     for k in range(len(size)):
         d.size[k], d.sstride[k], d.dstride[k] = int(size[k]), int(sstride[k]), int(dstride[k])

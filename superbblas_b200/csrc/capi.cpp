@@ -121,6 +121,7 @@ int sbb_sync_legacy_stream(const sbb_context *ctx) {
 int sbb_clear_caches(void) {
     SBB_TRY({
         clear_plan_cache();
+        permute_cache_clear();
         pool_clear();
     });
 }

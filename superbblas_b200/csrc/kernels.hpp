@@ -38,6 +38,9 @@ namespace sbb {
                       int dtype_dst, const double *alpha, bool add, int device, cudaStream_t stream,
                       std::string *describe = nullptr);
 
+    /// Drop the cached launches of permute_copy (and their device tables)
+    void permute_cache_clear();
+
     /// vr = alpha * sum_K f0(v0) f1(v1) + beta * vr. The current device must be `device`.
     void contract(const sbk_contract_desc &desc, int dtype, const double *alpha, const void *v0,
                   const void *v1, const double *beta, void *vr, int device, cudaStream_t stream,

@@ -29,6 +29,7 @@
 #include "kernels.hpp"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_runtime.h>
 #include <map>
@@ -38,20 +39,22 @@
 
 namespace sbb {
 
+    void permute_cache_clear();
+
     namespace {
 
         constexpr int KD = 8;   // dims handled inside one launch (after merging)
         constexpr int MAXT = 6; // tiled dims
         constexpr int NT = 256; // threads per CTA
-        constexpr int EPT = 8;  // slots (elements of a tile) per thread
+        constexpr int EPT = 8;  // slots (elements of a tile) per thread; 16 was measured slower for transposing tiles
 
         struct PermParams {
             int nd, nt, tile_elems, smem_elems;
+            int rot, rot_q; // rotation of the fastest dim in the destination, and its tiled-dim slot (-1: none)
             unsigned ntiles;
             int size[KD];
             int te[KD];
             unsigned ntile[KD];
-            unsigned delta[KD]; // gridDim.x decomposed on the tile grid
             long long tsstride[KD], tdstride[KD]; // te*stride: jump between tiles
             int tdim[MAXT];                       // tiled dims, destination order
             int text[MAXT];                       // their tile extents
@@ -151,10 +154,6 @@ namespace sbb {
 
         // ---- the kernel -------------------------------------------------------------------------
 
-        template <int N> struct SlotState {
-            unsigned so[N], dof[N], sp[N]; // element offsets inside the tile; sp = ld<<16 | st
-        };
-
         /// Decompose slot index e following the enumeration `ord` (positions in tdim[]).
         /// Returns false if e is outside the tile.
         __device__ __forceinline__ void slot_coords(const PermParams &p, unsigned e,
@@ -176,9 +175,17 @@ namespace sbb {
             }
         }
 
-        template <class Op, bool SMEM>
-        __global__ void __launch_bounds__(NT, 2)
-            permute_kernel(const __grid_constant__ PermParams p,
+        /// Per-geometry tables, built on the host once and cached on the device (see build_tables):
+        /// the slot maps of a tile and the origin of every tile.
+        struct Tables {
+            const unsigned *so, *dof, *sp; // per slot: source offset, destination offset, shared-memory
+                                           // positions (load position << 16 | store position)
+            const longlong2 *tiles;        // per tile: {source origin | boundary flag in bit 63, destination origin}
+        };
+
+        template <class Op, bool SMEM, int EPT, int MINB>
+        __global__ void __launch_bounds__(NT, MINB)
+            permute_kernel(const __grid_constant__ PermParams p, const Tables tab,
                            const typename Op::T *__restrict__ src, typename Op::Q *dst, Op op) {
             using T = typename Op::T;
             using Q = typename Op::Q;
@@ -186,11 +193,9 @@ namespace sbb {
             T *smem = reinterpret_cast<T *>(smem_raw);
 
             const unsigned tid = threadIdx.x;
-            int dord[MAXT];
-#pragma unroll
-            for (int q = 0; q < MAXT; ++q) dord[q] = q;
+            if (blockIdx.x >= p.ntiles) return;
 
-            // ---- per-slot maps, computed once -------------------------------------------------
+            // ---- per-slot maps: tile invariant, kept in registers ---------------------------------
             unsigned so[EPT], dof[EPT], sp[EPT];
             unsigned live = 0; // bit k set: slot k is inside the tile
 #pragma unroll
@@ -199,70 +204,40 @@ namespace sbb {
                 so[k] = dof[k] = sp[k] = 0;
                 if (e < (unsigned)p.tile_elems) {
                     live |= 1u << k;
-                    int c[MAXT];
-                    // store phase: destination enumeration
-                    slot_coords(p, e, dord, c);
-                    long long d = 0, s = 0;
-                    int pos = 0;
-#pragma unroll
-                    for (int q = 0; q < MAXT; ++q)
-                        if (q < p.nt) {
-                            d += c[q] * p.tds[q];
-                            s += c[q] * p.tss[q];
-                            pos += c[q] * p.smem_stride[q];
-                        }
-                    dof[k] = (unsigned)d;
-                    if (SMEM) {
-                        sp[k] = (unsigned)pos;
-                        // load phase: source enumeration
-                        slot_coords(p, e, p.sord, c);
-                        s = 0, pos = 0;
-#pragma unroll
-                        for (int q = 0; q < MAXT; ++q)
-                            if (q < p.nt) {
-                                s += c[q] * p.tss[q];
-                                pos += c[q] * p.smem_stride[q];
-                            }
-                        sp[k] |= (unsigned)pos << 16;
-                    }
-                    so[k] = (unsigned)s;
+                    so[k] = tab.so[e];
+                    dof[k] = tab.dof[e];
+                    if (SMEM) sp[k] = tab.sp[e];
                 }
             }
 
             // ---- tile loop, software pipelined -----------------------------------------------------
             // The loads of the next tile are in flight while the current tile is being stored, so a
             // CTA always has a tile's worth of bytes outstanding (HBM latency x bandwidth needs
-            // ~40 KB per SM in flight).
+            // ~40 KB per SM in flight).  Tile origins come from the table, two tiles ahead.
             struct Tile {
                 long long sbase, dbase;
                 unsigned mask_l, mask_s; // slots to load / to store (all live slots on full tiles)
             };
-            unsigned tc[KD];
-            {
-                unsigned t = blockIdx.x;
-#pragma unroll
-                for (int d = 0; d < KD; ++d) {
-                    tc[d] = 0;
-                    if (d < p.nd) {
-                        tc[d] = t % p.ntile[d];
-                        t /= p.ntile[d];
-                    }
-                }
-            }
-            auto tile_info = [&]() {
+            auto make_tile = [&](longlong2 e, unsigned tile) {
                 Tile t;
-                t.sbase = 0, t.dbase = 0;
-                bool full = true;
-#pragma unroll
-                for (int d = 0; d < KD; ++d)
-                    if (d < p.nd) {
-                        t.sbase += tc[d] * p.tsstride[d];
-                        t.dbase += tc[d] * p.tdstride[d];
-                        full = full && ((tc[d] + 1) * (unsigned)p.te[d] <= (unsigned)p.size[d]);
-                    }
+                t.sbase = e.x & 0x7fffffffffffffffll;
+                t.dbase = e.y;
                 t.mask_l = t.mask_s = live;
-                if (!full) {
-                    // boundary tile: mask the slots that fall outside the box
+                if (e.x < 0) {
+                    // boundary tile (rare): mask the slots that fall outside the box
+                    int dord[MAXT];
+#pragma unroll
+                    for (int q = 0; q < MAXT; ++q) dord[q] = q;
+                    unsigned tc[KD];
+                    unsigned rem = tile;
+#pragma unroll
+                    for (int d = 0; d < KD; ++d) {
+                        tc[d] = 0;
+                        if (d < p.nd) {
+                            tc[d] = rem % p.ntile[d];
+                            rem /= p.ntile[d];
+                        }
+                    }
                     int lim[MAXT];
 #pragma unroll
                     for (int q = 0; q < MAXT; ++q) {
@@ -276,9 +251,9 @@ namespace sbb {
                             lim[q] = min(p.text[q], p.size[d] - (int)(tcd * (unsigned)p.te[d]));
                         }
                     }
-                    auto inside = [&](unsigned e, const int *ord) {
+                    auto inside = [&](unsigned slot, const int *ord) {
                         int c[MAXT];
-                        slot_coords(p, e, ord, c);
+                        slot_coords(p, slot, ord, c);
                         bool ok = true;
 #pragma unroll
                         for (int q = 0; q < MAXT; ++q) ok = ok && (c[q] < lim[q]);
@@ -295,17 +270,6 @@ namespace sbb {
                 }
                 return t;
             };
-            auto advance = [&]() { // tc += delta with carries
-                unsigned carry = 0;
-#pragma unroll
-                for (int d = 0; d < KD; ++d)
-                    if (d < p.nd) {
-                        unsigned v = tc[d] + p.delta[d] + carry;
-                        carry = v >= p.ntile[d] ? 1u : 0u;
-                        if (carry) v -= p.ntile[d];
-                        tc[d] = v;
-                    }
-            };
             auto load = [&](const Tile &t, T(&r)[EPT]) {
                 const T *s = src + t.sbase;
 #pragma unroll
@@ -313,18 +277,18 @@ namespace sbb {
                     if (t.mask_l >> k & 1) r[k] = s[so[k]];
             };
 
-            if (blockIdx.x >= p.ntiles) return;
-            const unsigned my_tiles = (p.ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
-            Tile cur = tile_info();
+            const unsigned G = gridDim.x;
+            const unsigned my_tiles = (p.ntiles - blockIdx.x + G - 1) / G;
+            unsigned tile = blockIdx.x;
+            longlong2 e_nxt = my_tiles > 1 ? tab.tiles[tile + G] : tab.tiles[tile];
+            Tile cur = make_tile(tab.tiles[tile], tile);
             T r[EPT];
             load(cur, r);
-            for (unsigned i = 0; i < my_tiles; ++i) {
+            for (unsigned i = 0; i < my_tiles; ++i, tile += G) {
                 const bool has_next = i + 1 < my_tiles;
+                const longlong2 e_nn = i + 2 < my_tiles ? tab.tiles[tile + 2 * G] : e_nxt;
                 Tile nxt = cur;
-                if (has_next) {
-                    advance();
-                    nxt = tile_info();
-                }
+                if (has_next) nxt = make_tile(e_nxt, tile + G);
                 Q *w = dst + cur.dbase;
                 if (SMEM) {
 #pragma unroll
@@ -367,6 +331,7 @@ namespace sbb {
                     for (int k = 0; k < EPT; ++k) r[k] = r2[k];
                 }
                 cur = nxt;
+                e_nxt = e_nn;
             }
         }
 
@@ -432,6 +397,7 @@ namespace sbb {
             std::vector<int> size;
             std::vector<int64_t> ss, ds;
             int64_t soff = 0, doff = 0;
+            int rot = 0; ///< rotation of canonical dim 0 (which then has unit strides and is not merged)
         };
 
         Canon canonicalize(const sbk_box_desc &b, bool has_src) {
@@ -447,9 +413,14 @@ namespace sbb {
             }
             std::stable_sort(idx.begin(), idx.end(),
                              [&](int x, int y) { return b.dstride[x] < b.dstride[y]; });
+            if (b.rot != 0 && b.nd > 0 && b.size[0] > 1) {
+                if (!has_src || b.sstride[0] != 1 || b.dstride[0] != 1 || idx.empty() || idx[0] != 0)
+                    throw std::runtime_error("permute copy: rotation needs unit strides on dim 0");
+                c.rot = ((b.rot % b.size[0]) + b.size[0]) % b.size[0];
+            }
             for (int k : idx) {
                 const int64_t ss = has_src ? b.sstride[k] : 0, ds = b.dstride[k];
-                if (!c.size.empty()) {
+                if (!c.size.empty() && !(c.rot != 0 && c.size.size() == 1)) {
                     const int64_t n = c.size.back();
                     if (c.ds.back() * n == ds && c.ss.back() * n == ss &&
                         n * (int64_t)b.size[k] < (1ll << 30)) {
@@ -533,7 +504,91 @@ namespace sbb {
             int es = 0; // element size in bytes seen by the kernel
             int64_t run_d = 0, run_s = 0;
             bool empty = false;
+            Tables tab{nullptr, nullptr, nullptr, nullptr}; // device tables (owned by the launch cache)
+            void *tab_mem = nullptr;
+            int tab_device = -1;
         };
+
+        /// Host-side construction of the kernel's tables: the slot maps of one tile (load phase
+        /// enumerates along the source-contiguous direction, store phase along the destination-
+        /// contiguous one; `rot` rotates whole rows in the destination) and the origin of every
+        /// tile.  They depend on the geometry only, so they are built once per distinct copy,
+        /// uploaded and cached; the kernel then does no index arithmetic beyond one add per access.
+        void build_tables(LaunchPlan &lp, bool has_src, int device, cudaStream_t stream) {
+            const PermParams &p = lp.p;
+            const size_t ne = (size_t)p.tile_elems, nt = p.ntiles;
+            std::vector<unsigned> so(ne), dof(ne), sp(ne, 0);
+            auto coords = [&](size_t e, const int *ord, int *c) {
+                for (int q = 0; q < MAXT; ++q) c[q] = 0;
+                for (int q = 0; q < p.nt; ++q) {
+                    const int t = ord ? ord[q] : q;
+                    c[t] = (int)(e % (size_t)p.text[t]);
+                    e /= (size_t)p.text[t];
+                }
+            };
+            for (size_t e = 0; e < ne; ++e) {
+                int c[MAXT];
+                coords(e, nullptr, c); // destination enumeration
+                long long d = 0, sd = 0;
+                int pos = 0;
+                for (int q = 0; q < p.nt; ++q) {
+                    int cd = c[q];
+                    if (q == p.rot_q) cd = (cd + p.rot) % p.text[q];
+                    d += cd * p.tds[q];
+                    sd += c[q] * p.tss[q];
+                    pos += c[q] * p.smem_stride[q];
+                }
+                dof[e] = (unsigned)d;
+                so[e] = (unsigned)sd;
+                if (lp.smem) {
+                    coords(e, p.sord, c); // source enumeration
+                    long long ssrc = 0;
+                    int posl = 0;
+                    for (int q = 0; q < p.nt; ++q) {
+                        ssrc += c[q] * p.tss[q];
+                        posl += c[q] * p.smem_stride[q];
+                    }
+                    so[e] = (unsigned)ssrc;
+                    sp[e] = ((unsigned)posl << 16) | (unsigned)pos;
+                }
+            }
+            std::vector<long long> tiles(2 * nt);
+            {
+                unsigned tc[KD] = {0};
+                long long sb = 0, db = 0;
+                for (size_t t = 0; t < nt; ++t) {
+                    bool boundary = false;
+                    for (int d = 0; d < p.nd; ++d)
+                        if ((long long)(tc[d] + 1) * p.te[d] > p.size[d]) boundary = true;
+                    tiles[2 * t] = sb | (boundary ? (long long)(1ull << 63) : 0ll);
+                    tiles[2 * t + 1] = db;
+                    // next tile: increment the odometer
+                    for (int d = 0; d < p.nd; ++d) {
+                        sb += p.tsstride[d], db += p.tdstride[d];
+                        if (++tc[d] < p.ntile[d]) break;
+                        sb -= (long long)p.ntile[d] * p.tsstride[d];
+                        db -= (long long)p.ntile[d] * p.tdstride[d];
+                        tc[d] = 0;
+                    }
+                }
+            }
+            (void)has_src;
+            const size_t slot_bytes = (ne * sizeof(unsigned) + 255) / 256 * 256;
+            const size_t total = 3 * slot_bytes + tiles.size() * sizeof(long long);
+            char *mem = nullptr;
+            cuda_check(cudaMalloc((void **)&mem, total), "cudaMalloc (copy tables)");
+            cuda_check(cudaMemcpyAsync(mem, so.data(), ne * sizeof(unsigned), cudaMemcpyHostToDevice, stream), "table upload");
+            cuda_check(cudaMemcpyAsync(mem + slot_bytes, dof.data(), ne * sizeof(unsigned), cudaMemcpyHostToDevice, stream), "table upload");
+            cuda_check(cudaMemcpyAsync(mem + 2 * slot_bytes, sp.data(), ne * sizeof(unsigned), cudaMemcpyHostToDevice, stream), "table upload");
+            cuda_check(cudaMemcpyAsync(mem + 3 * slot_bytes, tiles.data(), tiles.size() * sizeof(long long), cudaMemcpyHostToDevice, stream), "table upload");
+            // pageable sources are staged before cudaMemcpyAsync returns, so the vectors may go away
+            lp.tab.so = (const unsigned *)mem;
+            lp.tab.dof = (const unsigned *)(mem + slot_bytes);
+            lp.tab.sp = (const unsigned *)(mem + 2 * slot_bytes);
+            lp.tab.tiles = (const longlong2 *)(mem + 3 * slot_bytes);
+            lp.tab_mem = mem;
+            lp.tab_device = device;
+        }
 
         /// Fill PermParams for a canonical box; `es` = bytes per element, `max_tile` = NT*EPT.
         LaunchPlan plan_launch(const Canon &c, int es, int max_tile, bool has_src) {
@@ -561,7 +616,15 @@ namespace sbb {
             // candidate search: maximise covered bytes per side (capped at 512 B), then tile size
             Tiling best;
             double best_score = -1;
-            for (int64_t wd = 1; wd <= max_tile; wd *= 2)
+            if (cc.rot != 0) {
+                // rotated rows: a tile holds whole rows
+                if (cc.size[0] > max_tile) throw std::runtime_error("permute copy: row too long to rotate");
+                best.te.assign(cc.nd, 1);
+                best.te[0] = cc.size[0];
+                best.total = best.run_d = best.run_s = cc.size[0];
+                best_score = 0;
+            }
+            for (int64_t wd = 1; wd <= max_tile && cc.rot == 0; wd *= 2)
                 for (int64_t ws = 1; ws <= max_tile; ws *= 2) {
                     Tiling t = build_tile(cc, sorder, dst_contig ? wd : 1, src_contig ? ws : 1);
                     if (t.total > max_tile) continue;
@@ -623,6 +686,8 @@ namespace sbb {
                     ++p.nt;
                 }
             p.tile_elems = (int)best.total;
+            p.rot = cc.rot;
+            p.rot_q = cc.rot != 0 ? 0 : -1; // dim 0 is tiled (te = size > 1), so it is tiled-dim slot 0
             // source enumeration order of the tiled dims
             std::vector<int> so(p.nt);
             std::iota(so.begin(), so.end(), 0);
@@ -644,17 +709,6 @@ namespace sbb {
             if (p.smem_elems > 65535) throw std::runtime_error("permute copy: tile too large");
             lp.run_d = best.run_d, lp.run_s = best.run_s;
             return lp;
-        }
-
-        void set_delta(PermParams &p, unsigned grid) {
-            unsigned t = grid;
-            for (int d = 0; d < KD; ++d) {
-                p.delta[d] = 0;
-                if (d < p.nd) {
-                    p.delta[d] = t % p.ntile[d];
-                    t /= p.ntile[d];
-                }
-            }
         }
 
         struct DevInfo {
@@ -681,7 +735,7 @@ namespace sbb {
             return std::max(n, 1);
         }
 
-        template <class Op>
+        template <class Op, int EPT_ = EPT>
         void launch_perm(LaunchPlan &lp, const void *src, void *dst, Op op, int device,
                          cudaStream_t stream) {
             using T = typename Op::T;
@@ -694,18 +748,17 @@ namespace sbb {
                 if (it == ctas.end()) it = ctas.emplace(smem_bytes, resident_ctas(kernel, smem_bytes)).first;
                 const unsigned grid = (unsigned)std::min<int64_t>(
                     lp.p.ntiles, (int64_t)dev_info(device).sms * it->second);
-                set_delta(lp.p, grid);
                 {
                     KernelTimer timer("permute", stream);
-                    kernel<<<grid, NT, smem_bytes, stream>>>(lp.p, (const T *)src, (Q *)dst, op);
+                    kernel<<<grid, NT, smem_bytes, stream>>>(lp.p, lp.tab, (const T *)src, (Q *)dst, op);
                 }
                 count_launch();
                 cuda_check(cudaGetLastError(), "permute_kernel launch");
             };
             if (lp.smem)
-                go(permute_kernel<Op, true>);
+                go(permute_kernel<Op, true, EPT_, 2>);
             else
-                go(permute_kernel<Op, false>);
+                go(permute_kernel<Op, false, EPT_, 2>);
         }
 
         template <class V>
@@ -725,7 +778,7 @@ namespace sbb {
             int f = 16 / es;
             for (; f > 1; f /= 2) {
                 bool ok = true;
-                if (c.size[0] % f) ok = false;
+                if (c.size[0] % f || c.rot % f) ok = false;
                 for (int d = 1; ok && d < c.nd; ++d)
                     if (c.ds[d] % f || (has_src && c.ss[d] % f)) ok = false;
                 if (ok && (c.doff % f || (has_src && c.soff % f))) ok = false;
@@ -735,6 +788,7 @@ namespace sbb {
                 if (ok) break;
             }
             if (f <= 1) return es;
+            c.rot /= f;
             c.size[0] /= f;
             for (int d = 1; d < c.nd; ++d) {
                 c.ds[d] /= f;
@@ -791,6 +845,16 @@ namespace sbb {
                    (dt0 == SBB_C64 && dt1 == SBB_C128) || (dt0 == SBB_C128 && dt1 == SBB_C64);
         }
 
+        struct Prepared {
+            Canon c;
+            LaunchPlan lp;
+            int es;
+        };
+        std::map<std::string, Prepared> &prepared_cache() {
+            static std::map<std::string, Prepared> cache;
+            return cache;
+        }
+
         /// Run one box of at most KD (canonical) dims
         void run_box(const Canon &c0, const void *src, int dt0, void *dst, int dt1,
                      const double *alpha, bool add, int device, cudaStream_t stream,
@@ -805,28 +869,25 @@ namespace sbb {
             // Prepared launches are cached by geometry, types, flags and pointer alignment: the
             // tiling search runs once per distinct copy (the reference caches its index vectors
             // the same way, tensor.h:946-951 -- here the cached object is ~0.5 KB, not the index).
-            struct Prepared {
-                Canon c;
-                LaunchPlan lp;
-                int es;
-            };
-            static std::map<std::string, Prepared> cache;
+            auto &cache = prepared_cache();
             std::string key;
             {
                 auto put = [&](const void *ptr, size_t n) { key.append((const char *)ptr, n); };
-                const int flags[6] = {dt0, dt1, is_zero, is_one, add,
-                                      (int)(((uintptr_t)src & 15) | (((uintptr_t)dst & 15) << 4))};
+                const int flags[7] = {dt0, dt1, is_zero, is_one, add,
+                                      (int)(((uintptr_t)src & 15) | (((uintptr_t)dst & 15) << 4)),
+                                      device};
                 put(flags, sizeof flags);
                 put(&c0.nd, sizeof c0.nd);
                 put(c0.size.data(), c0.size.size() * sizeof(int));
                 put(c0.ss.data(), c0.ss.size() * sizeof(int64_t));
                 put(c0.ds.data(), c0.ds.size() * sizeof(int64_t));
+                put(&c0.rot, sizeof c0.rot);
                 put(&c0.soff, sizeof c0.soff);
                 put(&c0.doff, sizeof c0.doff);
             }
             auto hit = describe ? cache.end() : cache.find(key);
             auto remember = [&](const Canon &cc, const LaunchPlan &lp, int es) {
-                if (cache.size() > 8192) cache.clear();
+                if (cache.size() > 8192) permute_cache_clear();
                 cache[key] = Prepared{cc, lp, es};
             };
             if (is_zero) {
@@ -858,7 +919,10 @@ namespace sbb {
                 } else {
                     es = promote(c, dtype_size(dt0), src, dst, true);
                     lp = plan_launch(c, es, max_tile_for(es), true);
-                    if (!describe) remember(c, lp, es);
+                    if (!describe) {
+                        build_tables(lp, true, device, stream);
+                        remember(c, lp, es);
+                    }
                 }
                 if (describe) {
                     ds << (lp.smem ? "move tiled" : "move direct") << " es=" << es
@@ -882,7 +946,10 @@ namespace sbb {
                 lp = hit->second.lp;
             } else {
                 lp = plan_launch(c, std::max(es0, es1), NT * EPT, true);
-                if (!describe) remember(c, lp, 0);
+                if (!describe) {
+                    build_tables(lp, true, device, stream);
+                    remember(c, lp, 0);
+                }
             }
             if (describe) {
                 ds << (lp.smem ? "typed tiled" : "typed direct") << " es=" << es0 << "->" << es1
@@ -913,6 +980,18 @@ namespace sbb {
         }
 
     } // namespace
+
+    void permute_cache_clear() {
+        for (auto &kv : prepared_cache()) {
+            LaunchPlan &lp = kv.second.lp;
+            if (lp.tab_mem) {
+                cudaSetDevice(lp.tab_device);
+                cudaDeviceSynchronize();
+                cudaFree(lp.tab_mem);
+            }
+        }
+        prepared_cache().clear();
+    }
 
     void permute_copy(const sbk_box_desc &box, const void *src, int dt0, void *dst, int dt1,
                       const double *alpha, bool add, int device, cudaStream_t stream,

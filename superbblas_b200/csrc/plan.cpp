@@ -134,7 +134,9 @@ namespace sbb {
             }
             for (int m = 0; m < n1; ++m) doff += (int64_t)(db.lfrom[m] + u[m] - db.u[m]) * dstr[m];
             for (int m : dim_order) {
-                if (len[m] == 1) continue;
+                // extent-1 dims are dropped, except the fastest one (kept so that the two halves of
+                // a wrapped row can be recognised and fused below)
+                if (len[m] == 1 && m != dim_order[0]) continue;
                 op.size.push_back(len[m]);
                 op.sstride.push_back(range_to_src[m] >= 0 ? sstr[i][range_to_src[m]] : 0);
                 op.dstride.push_back(dstr[m]);
@@ -237,6 +239,37 @@ namespace sbb {
             for (const auto &db : rest) emit_zero(j, db, dstr);
         }
 
+        // A periodic shift along the fastest label splits every row in two boxes (the part that
+        // stays and the part that wraps around); when both halves of the same rows are local they
+        // are fused back into one operation over whole rows with a rotation, so the rows are read
+        // and written contiguously once (instead of a second, badly coalesced pass for the slab
+        // that wrapped).
+        for (size_t i = 0; i < plan->ops.size(); ++i) {
+            BoxOp &A = plan->ops[i];
+            if (A.kind != BoxOp::Local || A.rot != 0 || A.size.empty()) continue;
+            if (A.sstride[0] != 1 || A.dstride[0] != 1) continue;
+            for (size_t j = 0; j < plan->ops.size(); ++j) {
+                BoxOp &B = plan->ops[j];
+                if (i == j || B.kind != BoxOp::Local || B.rot != 0) continue;
+                if (B.src_part != A.src_part || B.dst_part != A.dst_part) continue;
+                if (B.size.size() != A.size.size() || B.sstride != A.sstride ||
+                    B.dstride != A.dstride)
+                    continue;
+                bool same = true;
+                for (size_t d = 1; d < A.size.size(); ++d) same = same && A.size[d] == B.size[d];
+                if (!same) continue;
+                // A: src [0,n-r) -> dst [r,n);  B: src [n-r,n) -> dst [0,r)
+                if (B.soff != A.soff + A.size[0] || A.doff != B.doff + B.size[0]) continue;
+                if (A.size[0] + B.size[0] > 2048) continue; // a whole row must fit in one tile
+                A.rot = B.size[0];
+                A.size[0] += B.size[0];
+                A.doff = B.doff;
+                plan->ops.erase(plan->ops.begin() + j);
+                if (j < i) --i;
+                break;
+            }
+        }
+
         plan->send_elems = wire_out;
         plan->recv_elems = wire_in;
         for (int r = 0; r < a.nranks; ++r)
@@ -260,7 +293,7 @@ namespace sbb {
             for (auto s : op.sstride) ss << " " << s;
             ss << " dstride";
             for (auto s : op.dstride) ss << " " << s;
-            ss << "\n";
+            ss << " rot " << op.rot << "\n";
         }
         return ss.str();
     }

@@ -28,6 +28,7 @@ namespace sbb {
         Coor size;                        ///< extents
         std::vector<int64_t> sstride, dstride;
         int64_t soff = 0, doff = 0; ///< element offsets (for Pack/Unpack: inside the peer's segment)
+        int rot = 0; ///< rotation of the first listed dimension in the destination (see sbk_box_desc)
         int64_t volume() const { return sbb::volume(size); }
     };
 

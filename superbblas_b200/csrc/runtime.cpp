@@ -302,6 +302,7 @@ namespace sbb {
                 d.sstride[k] = op.sstride[k];
                 d.dstride[k] = op.dstride[k];
             }
+            d.rot = op.rot;
             return d;
         }
 

@@ -6,10 +6,14 @@ import numpy as np
 from oracle import oracle as O
 
 
-def _indices(size, stride, off):
+def _indices(size, stride, off, rot=0):
+    """Linear indices of a strided box; `rot` rotates the first listed dimension (sbk_box_desc)."""
     idx = np.full((1,), off, dtype=np.int64)
-    for n, s in zip(size, stride):
-        idx = (idx[:, None] + (np.arange(n, dtype=np.int64) * s)[None, :]).reshape(-1)
+    for k, (n, s) in enumerate(zip(size, stride)):
+        i = np.arange(n, dtype=np.int64)
+        if k == 0 and rot:
+            i = (i + rot) % n
+        idx = (idx[:, None] + (i * s)[None, :]).reshape(-1)
     return idx
 
 
@@ -50,7 +54,7 @@ def run_rank(ops, wire, rank, nranks, ncomp0, ncomp1, v0_local, v1_local, alpha,
             src = v0_local[op["src"] - rank * ncomp0]
             dst = v1_local[op["dst"] - rank * ncomp1]
             x = transformed(src[_indices(op["size"], op["sstride"], op["soff"])])
-            store(dst, _indices(op["size"], op["dstride"], op["doff"]), x, T)
+            store(dst, _indices(op["size"], op["dstride"], op["doff"], op.get("rot", 0)), x, T)
         elif op["kind"] == "unpack":
             dst = v1_local[op["dst"] - rank * ncomp1]
             x = recv[op["peer"]][_indices(op["size"], op["sstride"], op["soff"])]
