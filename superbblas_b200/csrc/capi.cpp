@@ -206,6 +206,7 @@ int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0
         dtype_bytes(dtype0);
         a.alpha_is_zero = is_zero(dtype0, alpha);
         a.wire_align = 16 / dtype_bytes((a.add && dtype0 != dtype1) ? dtype0 : dtype1);
+        a.chunk_bytes = exchange_chunk_bytes();
         auto plan = get_copy_plan(a);
         execute_copy(*plan, a, dtype0, dtype1, alpha, buffers(v0, ctx0, ncomponents0),
                      buffers((const void *const *)v1, ctx1, ncomponents1), c);
@@ -222,6 +223,7 @@ int sbb_copy_plan_describe(int elem_size1, int nd0, const int *p0, int ncomponen
                                     ncomponents1, o1, from1, dim1, nranks, rank, co, copyadd);
         a.alpha_is_zero = alpha_is_zero != 0;
         a.wire_align = elem_size1 > 0 && elem_size1 <= 16 ? 16 / elem_size1 : 1;
+        a.chunk_bytes = exchange_chunk_bytes();
         const std::string s = make_copy_plan(a)->describe();
         if (needed) *needed = s.size() + 1;
         if (s.size() + 1 > buflen) {

@@ -264,6 +264,7 @@ namespace sbb {
             ca.p1.assign((size_t)a.nranks * max_items, Box{Coor(ts.nd, 0), Coor(ts.nd, 0)});
             ca.nranks = a.nranks, ca.rank = me, ca.co = a.co;
             ca.wire_align = 16 / es;
+            ca.chunk_bytes = exchange_chunk_bytes();
             std::vector<int> slot(a.nranks, 0);
             std::vector<Buffer> dst(max_items);
             for (size_t q = 0; q < items.size(); ++q) {
@@ -364,6 +365,7 @@ namespace sbb {
             ra.p1 = a.tr.p, ra.ncomp1 = a.tr.ncomp, ra.from1 = a.tr.from, ra.dim1 = a.tr.dim;
             ra.nranks = a.nranks, ra.rank = me, ra.co = a.co, ra.add = true;
             ra.wire_align = 16 / es;
+            ra.chunk_bytes = exchange_chunk_bytes();
             std::vector<int> slot(a.nranks, 0);
             for (size_t q = 0; q < items.size(); ++q) {
                 const int r = items[q].part / tb.ncomp;

@@ -38,6 +38,9 @@ namespace sbb {
                       int dtype_dst, const double *alpha, bool add, int device, cudaStream_t stream,
                       std::string *describe = nullptr);
 
+    void set_grid_cap(int ctas);
+    int grid_cap();
+
     /// Drop the cached launches of permute_copy (and their device tables)
     void permute_cache_clear();
 

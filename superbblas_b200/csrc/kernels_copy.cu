@@ -42,6 +42,14 @@ namespace sbb {
     void permute_cache_clear();
 
     namespace {
+        int g_grid_cap = 0;
+    }
+    /// Upper bound on the CTAs of the copy kernels (0 = none).  While an exchange is in flight the
+    /// runtime leaves some SMs free so that NCCL's kernels can run beside the pack/unpack kernels.
+    void set_grid_cap(int ctas) { g_grid_cap = ctas; }
+    int grid_cap() { return g_grid_cap; }
+
+    namespace {
 
         constexpr int KD = 8;   // dims handled inside one launch (after merging)
         constexpr int MAXT = 6; // tiled dims
@@ -746,8 +754,9 @@ namespace sbb {
                 static std::map<size_t, int> ctas;
                 auto it = ctas.find(smem_bytes);
                 if (it == ctas.end()) it = ctas.emplace(smem_bytes, resident_ctas(kernel, smem_bytes)).first;
-                const unsigned grid = (unsigned)std::min<int64_t>(
+                unsigned grid = (unsigned)std::min<int64_t>(
                     lp.p.ntiles, (int64_t)dev_info(device).sms * it->second);
+                if (grid_cap() > 0) grid = std::min<unsigned>(grid, (unsigned)grid_cap());
                 {
                     KernelTimer timer("permute", stream);
                     kernel<<<grid, NT, smem_bytes, stream>>>(lp.p, lp.tab, (const T *)src, (Q *)dst, op);

@@ -141,34 +141,54 @@ namespace sbb {
                 op.sstride.push_back(range_to_src[m] >= 0 ? sstr[i][range_to_src[m]] : 0);
                 op.dstride.push_back(dstr[m]);
             }
-            const int64_t vol = volume(len);
             if (ri == me && rj == me) {
                 op.kind = BoxOp::Local;
                 op.src_comp = i % a.ncomp0, op.dst_comp = j % a.ncomp1;
                 op.soff = soff, op.doff = doff;
-            } else {
-                // compact, destination-ordered layout on the wire
-                std::vector<int64_t> wstr(op.size.size(), 1);
-                for (size_t d = 1; d < op.size.size(); ++d) wstr[d] = wstr[d - 1] * op.size[d - 1];
-                if (ri == me) {
-                    op.kind = BoxOp::Pack;
-                    op.peer = rj;
-                    op.src_comp = i % a.ncomp0;
-                    op.soff = soff;
-                    op.doff = wire_out[rj];
-                    op.dstride = wstr;
-                    wire_out[rj] = align_up(wire_out[rj] + vol, a.wire_align);
-                } else {
-                    op.kind = BoxOp::Unpack;
-                    op.peer = ri;
-                    op.dst_comp = j % a.ncomp1;
-                    op.doff = doff;
-                    op.soff = wire_in[ri];
-                    op.sstride = wstr;
-                    wire_in[ri] = align_up(wire_in[ri] + vol, a.wire_align);
-                }
+                plan->ops.push_back(std::move(op));
+                return;
             }
-            plan->ops.push_back(std::move(op));
+            // Remote: big boxes are cut along their slowest dimension so that the exchange can be
+            // pipelined (pack of piece k+1 and unpack of piece k-1 overlap the transfer of piece k).
+            // Sender and receiver cut identically (the rule only depends on the box).
+            const int64_t vol = volume(len);
+            const int64_t wire_es = 16 / std::max(1, a.wire_align);
+            int pieces = 1;
+            const int last = (int)op.size.size() - 1;
+            if (a.chunk_bytes > 0 && last >= 0 && vol * wire_es > a.chunk_bytes)
+                pieces = (int)std::min<int64_t>(op.size[last],
+                                                (vol * wire_es + a.chunk_bytes - 1) / a.chunk_bytes);
+            for (int pc = 0; pc < pieces; ++pc) {
+                BoxOp q = op;
+                int64_t lo = 0;
+                if (pieces > 1) {
+                    lo = (int64_t)op.size[last] * pc / pieces;
+                    const int64_t hi = (int64_t)op.size[last] * (pc + 1) / pieces;
+                    q.size[last] = (int)(hi - lo);
+                }
+                const int64_t pvol = volume(q.size);
+                // compact, destination-ordered layout on the wire
+                std::vector<int64_t> wstr(q.size.size(), 1);
+                for (size_t d = 1; d < q.size.size(); ++d) wstr[d] = wstr[d - 1] * q.size[d - 1];
+                if (ri == me) {
+                    q.kind = BoxOp::Pack;
+                    q.peer = rj;
+                    q.src_comp = i % a.ncomp0;
+                    q.soff = soff + (last >= 0 ? lo * op.sstride[last] : 0);
+                    q.doff = wire_out[rj];
+                    q.dstride = wstr;
+                    wire_out[rj] = align_up(wire_out[rj] + pvol, a.wire_align);
+                } else {
+                    q.kind = BoxOp::Unpack;
+                    q.peer = ri;
+                    q.dst_comp = j % a.ncomp1;
+                    q.doff = doff + (last >= 0 ? lo * op.dstride[last] : 0);
+                    q.soff = wire_in[ri];
+                    q.sstride = wstr;
+                    wire_in[ri] = align_up(wire_in[ri] + pvol, a.wire_align);
+                }
+                plan->ops.push_back(std::move(q));
+            }
         };
 
         auto emit_zero = [&](int j, const RBox &db, const std::vector<int64_t> &dstr) {
@@ -313,6 +333,7 @@ namespace sbb {
             };
             puti(a.nd0), puti(a.nd1), puti(a.ncomp0), puti(a.ncomp1), puti(a.nranks), puti(a.rank);
             puti(a.co), puti(a.add), puti(a.alpha_is_zero), puti(a.wire_align);
+            put(&a.chunk_bytes, sizeof a.chunk_bytes);
             k += a.o0, k += '|', k += a.o1, k += '|';
             putc(a.from0), putc(a.size0), putc(a.dim0), putc(a.from1), putc(a.dim1);
             for (const auto &b : a.p0) putc(b.from), putc(b.size);

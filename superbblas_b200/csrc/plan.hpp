@@ -53,6 +53,8 @@ namespace sbb {
         bool alpha_is_zero = false;
         /// Alignment, in elements of Q, of every box inside a message segment
         int wire_align = 1;
+        /// Remote boxes larger than this many bytes are cut in pieces (0 = never); see plan.cpp
+        int64_t chunk_bytes = 0;
     };
 
     /// Validate labels and sizes the way the reference does (toArray tensor.h:266, check_isomorphic

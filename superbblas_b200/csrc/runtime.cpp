@@ -1,6 +1,7 @@
 // Host runtime. See runtime.hpp.
 #include "runtime.hpp"
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <map>
@@ -83,6 +84,22 @@ namespace sbb {
     }
 
     void use_device(int device) { cuda_check(cudaSetDevice(device), "cudaSetDevice"); }
+
+    namespace {
+        std::vector<cudaEvent_t> g_round_events[MAX_DEVICES];
+        /// At least n reusable events on `device` (reuse across calls is safe: every wait on an
+        /// event is queued before the next call records it again)
+        std::vector<cudaEvent_t> &round_events(int device, int n) {
+            auto &v = g_round_events[device];
+            use_device(device);
+            while ((int)v.size() < n) {
+                cudaEvent_t e;
+                cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
+                v.push_back(e);
+            }
+            return v;
+        }
+    }
 
     DeviceState &device_state(int device) {
         if (device < 0 || device >= MAX_DEVICES) throw std::runtime_error("invalid device id");
@@ -184,6 +201,8 @@ namespace sbb {
             cudaStreamDestroy(s.comm_stream);
             cudaEventDestroy(s.ev_a);
             cudaEventDestroy(s.ev_b);
+            for (auto e : g_round_events[d]) cudaEventDestroy(e);
+            g_round_events[d].clear();
             s = DeviceState{};
         }
     }
@@ -262,6 +281,15 @@ namespace sbb {
         if (!c) return;
         if (c->nccl) nccl().CommDestroy(c->nccl);
         delete c;
+    }
+
+    int64_t exchange_chunk_bytes() {
+        static int64_t v = -1;
+        if (v < 0) {
+            const char *e = std::getenv("SBB_CHUNK_MB"), *b = std::getenv("SBB_CHUNK_BYTES");
+            v = b ? std::atoll(b) : (e ? std::atoll(e) : 256) * (1ll << 20);
+        }
+        return v;
     }
 
     int default_device(Comm *comm) {
@@ -470,52 +498,100 @@ namespace sbb {
             }
         };
 
-        auto exchange = [&]() {
-            // pack kernels (home stream) -> NCCL (comm stream)
-            use_device(home);
-            cuda_check(cudaEventRecord(hs.ev_a, hs.stream), "cudaEventRecord");
-            cuda_check(cudaStreamWaitEvent(hs.comm_stream, hs.ev_a, 0), "cudaStreamWaitEvent");
-            NcclApi &n = nccl();
-            nccl_check(n.GroupStart(), "ncclGroupStart");
-            for (int r = 0; r < plan.nranks; ++r) {
-                if (plan.send_elems[r] > 0)
-                    nccl_check(n.Send(sendbuf + seg_send[r], (size_t)plan.send_elems[r] * esw,
-                                      kNcclChar, r, comm->nccl, hs.comm_stream),
-                               "ncclSend");
-                if (plan.recv_elems[r] > 0)
-                    nccl_check(n.Recv(recvbuf + seg_recv[r], (size_t)plan.recv_elems[r] * esw,
-                                      kNcclChar, r, comm->nccl, hs.comm_stream),
-                               "ncclRecv");
-            }
-            nccl_check(n.GroupEnd(), "ncclGroupEnd");
-            cuda_check(cudaEventRecord(hs.ev_b, hs.comm_stream), "cudaEventRecord");
+        // ---- exchange, pipelined in rounds ------------------------------------------------------------
+        // A round is a window of `chunk` bytes of every peer's segment: the ops whose wire range
+        // starts inside it.  Round k: pack (compute stream) -> event -> grouped ncclSend/ncclRecv
+        // of that window (communication stream) -> event -> unpack.  All packs are queued first, so
+        // the transfer of round k overlaps the packing of rounds > k and the unpacking of rounds < k;
+        // the local part of a Copy is queued right after the first pack.  Sender and receiver derive
+        // the same rounds because they derive the same wire offsets.
+        const int64_t chunk = std::max<int64_t>(args.chunk_bytes, 1);
+        auto round_of = [&](const BoxOp &op) {
+            const int64_t off = (op.kind == BoxOp::Pack ? op.doff : op.soff) * esw;
+            return args.chunk_bytes > 0 ? (int)(off / chunk) : 0;
         };
-        auto wait_exchange = [&]() {
-            for (int a : devs) {
-                use_device(a);
-                cuda_check(cudaStreamWaitEvent(device_state(a).stream, hs.ev_b, 0),
-                           "cudaStreamWaitEvent");
-            }
-        };
-
         if (plan.needs_comm) {
+            // leave room for NCCL's kernels next to ours (SBB_COMM_GRID: CTAs of the copy kernels
+            // while an exchange is in flight; 0 = no limit)
+            static int comm_grid = -1;
+            if (comm_grid < 0) {
+                const char *e = std::getenv("SBB_COMM_GRID");
+                comm_grid = e ? std::atoi(e) : 0;
+            }
+            set_grid_cap(comm_grid);
+            int nrounds = 0;
             for (const auto &op : plan.ops)
-                if (op.kind == BoxOp::Pack) run(op);
-            exchange();
+                if (op.kind == BoxOp::Pack || op.kind == BoxOp::Unpack)
+                    nrounds = std::max(nrounds, round_of(op) + 1);
+            // byte window of every (round, peer): [lo, hi)
+            std::vector<std::vector<int64_t>> slo(nrounds, std::vector<int64_t>(plan.nranks, -1)),
+                shi = slo, rlo = slo, rhi = slo;
+            for (const auto &op : plan.ops) {
+                if (op.kind != BoxOp::Pack && op.kind != BoxOp::Unpack) continue;
+                const int k = round_of(op);
+                const bool snd = op.kind == BoxOp::Pack;
+                const int64_t b0 = (snd ? op.doff : op.soff) * esw, b1 = b0 + op.volume() * esw;
+                auto &lo = (snd ? slo : rlo)[k][op.peer];
+                auto &hi = (snd ? shi : rhi)[k][op.peer];
+                lo = lo < 0 ? b0 : std::min(lo, b0);
+                hi = std::max(hi, b1);
+            }
+            std::vector<cudaEvent_t> &evs = round_events(home, 2 * nrounds);
+            NcclApi &n = nccl();
+            bool local_done = false;
+            for (int k = 0; k < nrounds; ++k) {
+                for (const auto &op : plan.ops)
+                    if (op.kind == BoxOp::Pack && round_of(op) == k) run(op);
+                use_device(home);
+                cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
+                cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
+                nccl_check(n.GroupStart(), "ncclGroupStart");
+                for (int r = 0; r < plan.nranks; ++r) {
+                    if (slo[k][r] >= 0)
+                        nccl_check(n.Send(sendbuf + seg_send[r] + slo[k][r],
+                                          (size_t)(shi[k][r] - slo[k][r]), kNcclChar, r, comm->nccl,
+                                          hs.comm_stream),
+                                   "ncclSend");
+                    if (rlo[k][r] >= 0)
+                        nccl_check(n.Recv(recvbuf + seg_recv[r] + rlo[k][r],
+                                          (size_t)(rhi[k][r] - rlo[k][r]), kNcclChar, r, comm->nccl,
+                                          hs.comm_stream),
+                                   "ncclRecv");
+                }
+                nccl_check(n.GroupEnd(), "ncclGroupEnd");
+                cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
+                if (!args.add && !local_done) {
+                    // the local part overlaps the transfers
+                    for (const auto &op : plan.ops)
+                        if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
+                    local_done = true;
+                }
+            }
+            auto wait_round = [&](int k) {
+                for (int a : devs) {
+                    use_device(a);
+                    cuda_check(cudaStreamWaitEvent(device_state(a).stream, evs[2 * k + 1], 0),
+                               "cudaStreamWaitEvent");
+                }
+            };
             if (args.add) {
                 // additions are applied in plan order (ascending source part) so that the result
                 // does not depend on which contributions were remote
-                wait_exchange();
+                for (int k = 0; k < nrounds; ++k) wait_round(k);
                 for (const auto &op : plan.ops)
                     if (op.kind != BoxOp::Pack) run(op);
             } else {
-                // local part overlaps the transfer
-                for (const auto &op : plan.ops)
-                    if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
-                wait_exchange();
-                for (const auto &op : plan.ops)
-                    if (op.kind == BoxOp::Unpack) run(op);
+                if (!local_done)
+                    for (const auto &op : plan.ops)
+                        if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
+                for (int k = 0; k < nrounds; ++k) {
+                    wait_round(k);
+                    for (const auto &op : plan.ops)
+                        if (op.kind == BoxOp::Unpack && round_of(op) == k) run(op);
+                }
+                if (nrounds == 0) (void)0;
             }
+            set_grid_cap(0);
         } else {
             for (const auto &op : plan.ops) run(op);
         }

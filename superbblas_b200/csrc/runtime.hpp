@@ -52,6 +52,9 @@ namespace sbb {
 
     long long launch_count(bool reset);
 
+    /// Granularity of the pipelined exchange (bytes per peer and round); SBB_CHUNK_MB overrides
+    int64_t exchange_chunk_bytes();
+
     /// Default device for staging host buffers when no GPU component takes part
     int default_device(Comm *comm);
 

@@ -13,7 +13,8 @@ def launch(n, backend, cases, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "dist_check.py"), "--backend", backend, "--cases", str(cases)]
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+    # tiny pipeline pieces so that the cutting of remote boxes is exercised by the small test cases
+    env = dict(os.environ, OMP_NUM_THREADS="1", SBB_CHUNK_BYTES="256")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-3000:]

@@ -1,0 +1,163 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle cannot run
+at these sizes): round trips, agreement with torch index arithmetic on slices, linearity.  These
+sizes exceed 2^31 elements / 4 GiB per tensor, so they also pin the 64-bit offset paths."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import superbblas_b200 as sb
+
+
+@pytest.fixture(scope="module")
+def torch_gpu():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    if torch.cuda.get_device_properties(0).total_memory < 100 * 2 ** 30:
+        pytest.skip("needs a 180 GB B200")
+    return torch
+
+
+def _rand_complex(torch, n, dtype, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    real = torch.float64 if dtype == torch.complex128 else torch.float32
+    out = torch.empty(n, 2, device="cuda", dtype=real)
+    step = 1 << 28
+    for i in range(0, n, step):  # generate in slabs to bound temporaries
+        out[i:i + step].uniform_(-1, 1, generator=g)
+    return torch.view_as_complex(out)
+
+
+def test_config5_periodic_shift_full_size(torch_gpu):
+    """64^3 x 128 x (4,3) spin-colour field (BASELINE configs[4]), complex double = 6 GiB, 8 components
+    on z,t: shift by +1 in every direction, then by -1: identity; and the shifted field equals
+    torch.roll of the global field."""
+    torch = torch_gpu
+    P = 8
+    dim = [64, 64, 64, 128, 4, 3]
+    vol = int(np.prod(dim))
+    part = sb.basic_partitioning("xyztsc", dim, [1, 1, 2, 4, 1, 1], "zt", P, 1)
+    one = np.array([[[0] * 6, dim]], dtype=np.int32)
+    gpu = sb.createGpuContext(0)
+    glob = _rand_complex(torch, vol, torch.complex128, 1)
+    a = [torch.empty(int(np.prod(part[i, 1])), device="cuda", dtype=torch.complex128) for i in range(P)]
+    b = [torch.empty_like(x) for x in a]
+    # scatter the global field onto the 8 components
+    sb.copy(1, one, 1, "xyztsc", [0] * 6, dim, dim, [glob], None, gpu, part, P, "xyztsc", [0] * 6, dim,
+            a, None, gpu, sb.FastToSlow, sb.Copy)
+    shift = [1, 1, 1, 1, 0, 0]
+    sb.copy(1, part, P, "xyztsc", [0] * 6, dim, dim, a, None, gpu, part, P, "xyztsc", shift, dim, b,
+            None, gpu, sb.FastToSlow, sb.Copy)
+    # gather b back and compare with torch.roll
+    back = torch.empty_like(glob)
+    sb.copy(1, part, P, "xyztsc", [0] * 6, dim, dim, b, None, gpu, one, 1, "xyztsc", [0] * 6, dim,
+            [back], None, gpu, sb.FastToSlow, sb.Copy)
+    sb.sync(gpu)
+    ref = torch.roll(glob.view(*reversed(dim)), shifts=(1, 1, 1, 1), dims=(2, 3, 4, 5)).reshape(-1)
+    assert torch.equal(torch.view_as_real(back), torch.view_as_real(ref))
+    del ref
+    # shift back: identity
+    inv = [dim[k] - shift[k] if shift[k] else 0 for k in range(6)]
+    sb.copy(1, part, P, "xyztsc", [0] * 6, dim, dim, b, None, gpu, part, P, "xyztsc", inv, dim, a,
+            None, gpu, sb.FastToSlow, sb.Copy)
+    sb.copy(1, part, P, "xyztsc", [0] * 6, dim, dim, a, None, gpu, one, 1, "xyztsc", [0] * 6, dim,
+            [back], None, gpu, sb.FastToSlow, sb.Copy)
+    sb.sync(gpu)
+    assert torch.equal(torch.view_as_real(back), torch.view_as_real(glob))
+
+
+def test_config3_redistribution_full_size(torch_gpu):
+    """32^3 x 64 x (4,3) x 128 complex float = 3.2e9 elements (24 GiB, BASELINE configs[2]) from
+    t-slabs to (z,t) blocks with 8 components on one GPU, and back: identity; plus spot checks of
+    the block contents against index arithmetic."""
+    torch = torch_gpu
+    P = 8
+    dim = [32, 32, 32, 64, 4, 3, 128]
+    p0 = sb.basic_partitioning("xyztscn", dim, [1, 1, 1, P, 1, 1, 1], "t", P, 1)
+    p1 = sb.basic_partitioning("xyztscn", dim, [1, 1, 2, P // 2, 1, 1, 1], "zt", P, 1)
+    gpu = sb.createGpuContext(0)
+    a = [_rand_complex(torch, int(np.prod(p0[i, 1])), torch.complex64, 10 + i) for i in range(P)]
+    b = [torch.zeros(int(np.prod(p1[i, 1])), device="cuda", dtype=torch.complex64) for i in range(P)]
+    sb.copy(1, p0, P, "xyztscn", [0] * 7, dim, dim, a, None, gpu, p1, P, "xyztscn", [0] * 7, dim, b,
+            None, gpu, sb.FastToSlow, sb.Copy)
+    sb.sync(gpu)
+    # spot check: destination block j=(jz,jt) holds z in [16 jz, 16 jz+16), t in [16 jt, 16 jt+16)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        c = [int(rng.integers(0, d)) for d in dim]
+        i = c[3] // 8                       # source slab (t extent 8)
+        j = 4 * (c[2] // 16) + c[3] // 16   # destination block
+        ls = [c[0], c[1], c[2], c[3] - 8 * i, c[4], c[5], c[6]]
+        ld = [c[0], c[1], c[2] - 16 * (c[2] // 16), c[3] - 16 * (c[3] // 16), c[4], c[5], c[6]]
+        isrc = sum(x * s for x, s in zip(ls, np.cumprod([1] + list(p0[i, 1][:-1]), dtype=np.int64)))
+        idst = sum(x * s for x, s in zip(ld, np.cumprod([1] + list(p1[j, 1][:-1]), dtype=np.int64)))
+        assert a[i][int(isrc)].item() == b[j][int(idst)].item()
+    a2 = [torch.zeros_like(x) for x in a]
+    sb.copy(1, p1, P, "xyztscn", [0] * 7, dim, dim, b, None, gpu, p0, P, "xyztscn", [0] * 7, dim, a2,
+            None, gpu, sb.FastToSlow, sb.Copy)
+    sb.sync(gpu)
+    for x, y in zip(a, a2):
+        assert torch.equal(torch.view_as_real(x), torch.view_as_real(y))
+
+
+def test_single_tensor_beyond_2G_elements(torch_gpu):
+    """One component with 3.2e9 complex-float elements (> 2^31): permutation "xyztscn" -> "nxyztsc"
+    and back is the identity, and slices agree with torch."""
+    torch = torch_gpu
+    dim0 = [32, 32, 32, 64, 4, 3, 128]
+    o0, o1 = "xyztscn", "nscxyzt"
+    dim1 = [dim0[o0.index(l)] for l in o1]
+    vol = int(np.prod(dim0))
+    assert vol > 2 ** 31
+    gpu = sb.createGpuContext(0)
+    p0 = np.array([[[0] * 7, dim0]], dtype=np.int32)
+    p1 = np.array([[[0] * 7, dim1]], dtype=np.int32)
+    a = _rand_complex(torch, vol, torch.complex64, 3)
+    b = torch.zeros_like(a)
+    sb.copy(1, p0, 1, o0, [0] * 7, dim0, dim0, [a], None, gpu, p1, 1, o1, [0] * 7, dim1, [b], None,
+            gpu, sb.FastToSlow, sb.Copy)
+    sb.sync(gpu)
+    # b[n + 128*(s + 4*(c + 3*site))] == a[site + V*(s + 4*(c + 3*n))]
+    V = 32 * 32 * 32 * 64
+    A = a.view(128, 3, 4, V)         # [n][c][s][site]
+    B = b.view(V, 3, 4, 128)         # [site][c][s][n]
+    for site in (0, 1, V // 2 + 17, V - 1):
+        assert torch.equal(torch.view_as_real(B[site]), torch.view_as_real(A[:, :, :, site].permute(1, 2, 0).contiguous()))
+    c = torch.zeros_like(a)
+    sb.copy(1, p1, 1, o1, [0] * 7, dim1, dim1, [b], None, gpu, p0, 1, o0, [0] * 7, dim0, [c], None,
+            gpu, sb.FastToSlow, sb.Copy)
+    sb.sync(gpu)
+    assert torch.equal(torch.view_as_real(a), torch.view_as_real(c))
+
+
+def test_config2_contraction_full_size(torch_gpu):
+    """BASELINE configs[1] at full size (2 x 6 GiB operands): every time slice against a cuBLAS
+    evaluation in complex128, 1e-12 relative; plus linearity in alpha/beta."""
+    torch = torch_gpu
+    L, Lt, nv = 32, 64, 64
+    K = 3 * L ** 3
+    dimv, dimr = [3, L, L, L, Lt, nv], [Lt, nv, nv]
+    pv = np.array([[[0] * 6, dimv]], dtype=np.int32)
+    pr = np.array([[[0] * 3, dimr]], dtype=np.int32)
+    gpu = sb.createGpuContext(0)
+    a = _rand_complex(torch, K * Lt * nv, torch.complex128, 5)
+    b = _rand_complex(torch, K * Lt * nv, torch.complex128, 6)
+    r = torch.zeros(Lt * nv * nv, device="cuda", dtype=torch.complex128)
+    sb.contraction(1, pv, [0] * 6, dimv, dimv, 1, "cxyztn", True, [a], gpu, pv, [0] * 6, dimv, dimv, 1,
+                   "cxyztm", False, [b], gpu, 0, pr, [0] * 3, dimr, dimr, 1, "tnm", [r], gpu,
+                   sb.FastToSlow)
+    sb.sync(gpu)
+    A, B, R = a.view(nv, Lt, K), b.view(nv, Lt, K), r.view(nv, nv, Lt)  # R[m][n][t]
+    worst = 0.0
+    for t in range(Lt):
+        ref = B[:, t, :] @ A[:, t, :].conj().T  # [m][n]
+        worst = max(worst, (torch.linalg.norm(R[:, :, t] - ref) / torch.linalg.norm(ref)).item())
+    assert worst < 1e-12, worst
+    r2 = r.clone()
+    sb.contraction(2 - 1j, pv, [0] * 6, dimv, dimv, 1, "cxyztn", True, [a], gpu, pv, [0] * 6, dimv,
+                   dimv, 1, "cxyztm", False, [b], gpu, 0.5, pr, [0] * 3, dimr, dimr, 1, "tnm", [r2],
+                   gpu, sb.FastToSlow)
+    sb.sync(gpu)
+    want = (2 - 1j) * r + 0.5 * r
+    assert (torch.linalg.norm(r2 - want) / torch.linalg.norm(want)).item() < 1e-12

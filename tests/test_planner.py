@@ -1,8 +1,12 @@
 """Host logic without a GPU: the copy planner (geometry in range space, exactly-once Copy, ordered
 Add, zero-fill of unsupported destinations, message layout) against the oracle, for one rank and
 for several ranks simulated in one process."""
+import os
+
 import numpy as np
 import pytest
+
+os.environ.setdefault("SBB_CHUNK_BYTES", "192")  # cut remote boxes in pieces even in small cases
 
 import superbblas_b200 as sb
 from tests import cases as C
