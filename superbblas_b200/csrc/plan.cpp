@@ -117,13 +117,17 @@ namespace sbb {
         std::vector<int> dim_order(n1);
         for (int m = 0; m < n1; ++m) dim_order[m] = a.co == FastToSlow ? m : n1 - 1 - m;
 
-        // per (sender, receiver) running offsets inside the message, for the pairs that involve me
-        std::vector<int64_t> wire_out(a.nranks, 0), wire_in(a.nranks, 0);
+        // running length (elements on the wire) of the message of every (sender, receiver) pair; all
+        // pairs are tracked, not only mine, because the peer-memory transport needs to know where my
+        // segment starts inside each receiver's arena
+        std::vector<int64_t> pair((size_t)a.nranks * a.nranks, 0);
+        auto wire = [&](int from, int to) -> int64_t & { return pair[(size_t)from * a.nranks + to]; };
 
         auto emit = [&](int i, int j, const RBox &sb, const RBox &db, const Coor &u,
                         const Coor &len, const std::vector<int64_t> &dstr) {
             const int ri = i / a.ncomp0, rj = j / a.ncomp1;
-            if (ri != me && rj != me) return;
+            const bool mine = ri == me || rj == me;
+            if (ri == rj && !mine) return;
             BoxOp op;
             op.src_part = i, op.dst_part = j;
             int64_t soff = 0, doff = 0;
@@ -170,22 +174,24 @@ namespace sbb {
                 // compact, destination-ordered layout on the wire
                 std::vector<int64_t> wstr(q.size.size(), 1);
                 for (size_t d = 1; d < q.size.size(); ++d) wstr[d] = wstr[d - 1] * q.size[d - 1];
+                int64_t &w = wire(ri, rj);
+                const int64_t at = w;
+                w = align_up(w + pvol, a.wire_align);
+                if (!mine) continue;
                 if (ri == me) {
                     q.kind = BoxOp::Pack;
                     q.peer = rj;
                     q.src_comp = i % a.ncomp0;
                     q.soff = soff + (last >= 0 ? lo * op.sstride[last] : 0);
-                    q.doff = wire_out[rj];
+                    q.doff = at;
                     q.dstride = wstr;
-                    wire_out[rj] = align_up(wire_out[rj] + pvol, a.wire_align);
                 } else {
                     q.kind = BoxOp::Unpack;
                     q.peer = ri;
                     q.dst_comp = j % a.ncomp1;
                     q.doff = doff + (last >= 0 ? lo * op.dstride[last] : 0);
-                    q.soff = wire_in[ri];
+                    q.soff = at;
                     q.sstride = wstr;
-                    wire_in[ri] = align_up(wire_in[ri] + pvol, a.wire_align);
                 }
                 plan->ops.push_back(std::move(q));
             }
@@ -290,10 +296,26 @@ namespace sbb {
             }
         }
 
-        plan->send_elems = wire_out;
-        plan->recv_elems = wire_in;
-        for (int r = 0; r < a.nranks; ++r)
-            if (wire_out[r] > 0 || wire_in[r] > 0) plan->needs_comm = true;
+        plan->send_seg_off.assign(a.nranks, 0);
+        plan->recv_seg_off.assign(a.nranks, 0);
+        const int seg_align = 16 * std::max(1, a.wire_align); // 256 bytes
+        for (int r = 0; r < a.nranks; ++r) {
+            plan->send_elems[r] = wire(me, r);
+            plan->recv_elems[r] = wire(r, me);
+            if (wire(me, r) > 0 || wire(r, me) > 0) plan->needs_comm = true;
+        }
+        // layout of every rank's arena: one 256-byte aligned segment per sender, in rank order
+        for (int q = 0; q < a.nranks; ++q) {
+            int64_t off = 0;
+            for (int r = 0; r < a.nranks; ++r) {
+                if (q == me) plan->recv_seg_off[r] = off;
+                if (r == me) plan->send_seg_off[q] = off;
+                off += align_up(wire(r, q), seg_align);
+                if (wire(r, q) > 0) plan->any_comm = true;
+                plan->max_pair_elems = std::max(plan->max_pair_elems, wire(r, q));
+            }
+            plan->arena_elems = std::max(plan->arena_elems, off);
+        }
         return plan;
     }
 

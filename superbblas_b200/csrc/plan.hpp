@@ -37,7 +37,13 @@ namespace sbb {
         int nranks = 1, rank = 0;
         /// Elements of Q exchanged with each rank (index = peer rank)
         std::vector<int64_t> send_elems, recv_elems;
-        bool needs_comm = false;
+        bool needs_comm = false; ///< this rank sends or receives something
+        bool any_comm = false;   ///< some rank does (all ranks agree on this one)
+        /// Peer-memory transport: element offset of my segment inside receiver q's arena, of sender
+        /// r's segment inside mine, and the largest arena any rank needs (all ranks agree)
+        std::vector<int64_t> send_seg_off, recv_seg_off;
+        int64_t arena_elems = 0;
+        int64_t max_pair_elems = 0; ///< longest message of the whole exchange (all ranks agree)
         std::string describe() const;
     };
 

@@ -114,6 +114,8 @@ namespace sbb {
             d.id = device;
             cuda_check(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "stream");
             cuda_check(cudaStreamCreateWithFlags(&d.comm_stream, cudaStreamNonBlocking), "stream");
+            cuda_check(cudaStreamCreateWithFlags(&d.aux_stream, cudaStreamNonBlocking), "stream");
+            cuda_check(cudaEventCreateWithFlags(&d.ev_c, cudaEventDisableTiming), "event");
             cuda_check(cudaEventCreateWithFlags(&d.ev_a, cudaEventDisableTiming), "event");
             cuda_check(cudaEventCreateWithFlags(&d.ev_b, cudaEventDisableTiming), "event");
         }
@@ -197,8 +199,11 @@ namespace sbb {
             use_device(d);
             cudaStreamSynchronize(s.stream);
             cudaStreamSynchronize(s.comm_stream);
+            cudaStreamSynchronize(s.aux_stream);
             cudaStreamDestroy(s.stream);
             cudaStreamDestroy(s.comm_stream);
+            cudaStreamDestroy(s.aux_stream);
+            cudaEventDestroy(s.ev_c);
             cudaEventDestroy(s.ev_a);
             cudaEventDestroy(s.ev_b);
             for (auto e : g_round_events[d]) cudaEventDestroy(e);
@@ -222,6 +227,8 @@ namespace sbb {
             int (*CommDestroy)(void *) = nullptr;
             int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
             int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+            int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+            int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
             int (*GroupStart)() = nullptr;
             int (*GroupEnd)() = nullptr;
             const char *(*GetErrorString)(int) = nullptr;
@@ -248,6 +255,8 @@ namespace sbb {
             api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
             api.Send = (decltype(api.Send))sym("ncclSend");
             api.Recv = (decltype(api.Recv))sym("ncclRecv");
+            api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+            api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
             api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
             api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
             api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
@@ -259,9 +268,80 @@ namespace sbb {
                                          nccl().GetErrorString(r));
         }
         constexpr int kNcclChar = 0; // ncclInt8 / ncclChar
+        constexpr int kNcclInt32 = 2, kNcclSum = 0, kNcclMin = 3;
     }
 
     void nccl_unique_id(void *id128) { nccl_check(nccl().GetUniqueId(id128), "ncclGetUniqueId"); }
+
+    namespace {
+        /// All ranks agree on min(value) (used to decide collectively whether a step worked)
+        int agree_min(Comm *c, int value) {
+            DeviceState &d = device_state(c->device);
+            use_device(c->device);
+            cuda_check(cudaMemcpyAsync(c->flag, &value, sizeof(int), cudaMemcpyHostToDevice, d.comm_stream), "memcpy");
+            nccl_check(nccl().AllReduce(c->flag, c->flag, 1, kNcclInt32, kNcclMin, c->nccl, d.comm_stream), "ncclAllReduce");
+            int out = 0;
+            cuda_check(cudaMemcpyAsync(&out, c->flag, sizeof(int), cudaMemcpyDeviceToHost, d.comm_stream), "memcpy");
+            cuda_check(cudaStreamSynchronize(d.comm_stream), "cudaStreamSynchronize");
+            return out;
+        }
+
+        void release_arena(Comm *c) {
+            use_device(c->device);
+            for (int r = 0; r < (int)c->peer.size(); ++r)
+                if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+            c->peer.clear();
+            if (c->arena) cudaFree(c->arena);
+            c->arena = nullptr, c->half_bytes = 0;
+        }
+
+        /// Make every rank's arena at least 2 x half_bytes and map it everywhere. Collective.
+        void ensure_arena(Comm *c, size_t half_bytes) {
+            if (half_bytes <= c->half_bytes) return;
+            DeviceState &d = device_state(c->device);
+            use_device(c->device);
+            // nobody may still be using the old arenas
+            cuda_check(cudaStreamSynchronize(d.stream), "cudaStreamSynchronize");
+            agree_min(c, 1);
+            release_arena(c);
+            half_bytes = (half_bytes + half_bytes / 4 + (1 << 20) - 1) >> 20 << 20; // grow with slack
+            int ok = cudaMalloc((void **)&c->arena, 2 * half_bytes) == cudaSuccess ? 1 : 0;
+            if (!ok) cudaGetLastError(), c->arena = nullptr;
+            cudaIpcMemHandle_t mine;
+            std::memset(&mine, 0, sizeof mine);
+            if (ok && cudaIpcGetMemHandle(&mine, c->arena) != cudaSuccess) cudaGetLastError(), ok = 0;
+            // exchange the handles with an all-gather (they are 64 opaque bytes each)
+            char *dev = nullptr;
+            cuda_check(cudaMalloc((void **)&dev, sizeof(mine) * (c->nranks + 1)), "cudaMalloc");
+            cuda_check(cudaMemcpyAsync(dev, &mine, sizeof mine, cudaMemcpyHostToDevice, d.comm_stream), "memcpy");
+            nccl_check(nccl().AllGather(dev, dev + sizeof mine, sizeof mine, kNcclChar, c->nccl, d.comm_stream), "ncclAllGather");
+            std::vector<cudaIpcMemHandle_t> all(c->nranks);
+            cuda_check(cudaMemcpyAsync(all.data(), dev + sizeof mine, sizeof(mine) * c->nranks, cudaMemcpyDeviceToHost, d.comm_stream), "memcpy");
+            cuda_check(cudaStreamSynchronize(d.comm_stream), "cudaStreamSynchronize");
+            cudaFree(dev);
+            ok = agree_min(c, ok);
+            c->peer.assign(c->nranks, nullptr);
+            for (int r = 0; ok && r < c->nranks; ++r) {
+                if (r == c->rank) {
+                    c->peer[r] = c->arena;
+                    continue;
+                }
+                void *p = nullptr;
+                if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = 0;
+                }
+                c->peer[r] = (char *)p;
+            }
+            ok = agree_min(c, ok);
+            if (!ok) {
+                release_arena(c);
+                c->p2p = false; // every rank takes this branch: fall back to ncclSend/ncclRecv
+                return;
+            }
+            c->half_bytes = half_bytes;
+        }
+    }
 
     Comm *comm_create(const void *id128, int nranks, int rank, int device) {
         if (nranks < 1 || rank < 0 || rank >= nranks) throw std::runtime_error("invalid rank");
@@ -273,13 +353,25 @@ namespace sbb {
             Id128 id;
             std::memcpy(id.bytes, id128, 128);
             nccl_check(nccl().CommInitRank(&c->nccl, nranks, id, rank), "ncclCommInitRank");
+            cuda_check(cudaMalloc((void **)&c->flag, 256), "cudaMalloc");
+            const char *e = std::getenv("SBB_P2P");
+            c->p2p = !(e && std::atoi(e) == 0);
+            // every rank must take the same decision
+            c->p2p = agree_min(c, c->p2p ? 1 : 0) != 0;
         }
         return c;
     }
 
     void comm_destroy(Comm *c) {
         if (!c) return;
-        if (c->nccl) nccl().CommDestroy(c->nccl);
+        if (c->nccl) {
+            use_device(c->device);
+            cudaStreamSynchronize(device_state(c->device).stream);
+            cudaStreamSynchronize(device_state(c->device).comm_stream);
+            release_arena(c);
+            if (c->flag) cudaFree(c->flag);
+            nccl().CommDestroy(c->nccl);
+        }
         delete c;
     }
 
@@ -347,7 +439,8 @@ namespace sbb {
     void execute_copy(const CopyPlan &plan, const CopyArgs &args, int dtype0, int dtype1,
                       const double *alpha, const std::vector<Buffer> &v0,
                       const std::vector<Buffer> &v1, Comm *comm) {
-        if (plan.ops.empty()) return;
+        // a rank without work still takes part in the barrier of the peer-memory transport
+        if (plan.ops.empty() && !(comm && comm->nccl && comm->p2p && plan.any_comm)) return;
         const int es0 = dtype_bytes(dtype0), es1 = dtype_bytes(dtype1);
         // Element type on the wire: the destination type, so that conversions happen once, before
         // sending (as the reference does, dist.h:1450-1451) -- except when adding with a type
@@ -443,10 +536,15 @@ namespace sbb {
         };
         cross_sync(true);
 
+        // Peer-memory transport: all ranks take the same decision from plan-wide quantities
+        const bool p2p = comm && comm->nccl && comm->p2p && plan.any_comm;
+        if (p2p) ensure_arena(comm, (size_t)plan.arena_elems * esw);
+        const bool use_p2p = p2p && comm->p2p; // ensure_arena may have disabled it (collectively)
+
         // Message buffers: one 256-byte aligned segment per peer
         std::vector<size_t> seg_send(plan.nranks + 1, 0), seg_recv(plan.nranks + 1, 0);
         char *sendbuf = nullptr, *recvbuf = nullptr;
-        if (plan.needs_comm) {
+        if (plan.needs_comm && !use_p2p) {
             for (int r = 0; r < plan.nranks; ++r) {
                 seg_send[r + 1] = seg_send[r] + ((size_t)plan.send_elems[r] * esw + 255) / 256 * 256;
                 seg_recv[r + 1] = seg_recv[r] + ((size_t)plan.recv_elems[r] * esw + 255) / 256 * 256;
@@ -455,7 +553,23 @@ namespace sbb {
             if (seg_recv[plan.nranks]) recvbuf = (char *)pool_alloc(home, seg_recv[plan.nranks]);
         }
 
+        std::vector<char *> p2p_send_base(plan.nranks, nullptr), p2p_recv_base(plan.nranks, nullptr);
+        if (use_p2p) {
+            const size_t half = (comm->epoch & 1) * comm->half_bytes;
+            for (int r = 0; r < plan.nranks; ++r) {
+                p2p_send_base[r] = comm->peer[r] + half + (size_t)plan.send_seg_off[r] * esw;
+                p2p_recv_base[r] = comm->arena + half + (size_t)plan.recv_seg_off[r] * esw;
+            }
+            ++comm->epoch;
+        }
         const double one[2] = {1, 0}, zero[2] = {0, 0};
+        // kernels that write the destination normally go to the destination device's stream; during a
+        // peer-memory exchange those of the home device go to its auxiliary stream so that they run
+        // beside the (NVLink-bound) pack kernels
+        bool use_aux = false;
+        auto stream_for = [&](int dev) {
+            return use_aux && dev == home ? hs.aux_stream : device_state(dev).stream;
+        };
         auto run = [&](const BoxOp &op) {
             sbk_box_desc desc = to_desc(op);
             switch (op.kind) {
@@ -465,7 +579,7 @@ namespace sbb {
                 use_device(b.device);
                 desc.soff = op.soff, desc.doff = op.doff;
                 permute_copy(desc, a.ptr, dtype0, b.ptr, dtype1, alpha, args.add, b.device,
-                             device_state(b.device).stream);
+                             stream_for(b.device));
                 break;
             }
             case BoxOp::Pack: {
@@ -473,9 +587,10 @@ namespace sbb {
                 enable_peer(home, a.device);
                 use_device(home);
                 desc.soff = op.soff, desc.doff = op.doff;
-                // scaled (and normally converted) before it leaves
-                permute_copy(desc, a.ptr, dtype0, sendbuf + seg_send[op.peer], wire_dtype, alpha,
-                             false, home, hs.stream);
+                // scaled (and normally converted) before it leaves; with the peer-memory transport
+                // the kernel's stores go straight into the receiver's arena over NVLink
+                char *to = use_p2p ? p2p_send_base[op.peer] : sendbuf + seg_send[op.peer];
+                permute_copy(desc, a.ptr, dtype0, to, wire_dtype, alpha, false, home, hs.stream);
                 break;
             }
             case BoxOp::Unpack: {
@@ -483,8 +598,9 @@ namespace sbb {
                 enable_peer(b.device, home);
                 use_device(b.device);
                 desc.soff = op.soff, desc.doff = op.doff;
-                permute_copy(desc, recvbuf + seg_recv[op.peer], wire_dtype, b.ptr, dtype1, one,
-                             args.add, b.device, device_state(b.device).stream);
+                const char *from = use_p2p ? p2p_recv_base[op.peer] : recvbuf + seg_recv[op.peer];
+                permute_copy(desc, from, wire_dtype, b.ptr, dtype1, one, args.add, b.device,
+                             stream_for(b.device));
                 break;
             }
             case BoxOp::Zero: {
@@ -492,7 +608,7 @@ namespace sbb {
                 use_device(b.device);
                 desc.doff = op.doff;
                 permute_copy(desc, nullptr, dtype1, b.ptr, dtype1, zero, false, b.device,
-                             device_state(b.device).stream);
+                             stream_for(b.device));
                 break;
             }
             }
@@ -510,7 +626,77 @@ namespace sbb {
             const int64_t off = (op.kind == BoxOp::Pack ? op.doff : op.soff) * esw;
             return args.chunk_bytes > 0 ? (int)(off / chunk) : 0;
         };
-        if (plan.needs_comm) {
+        if (use_p2p) {
+            // ---- peer-memory exchange --------------------------------------------------------------
+            // pack kernels write into the receivers' arenas; one small all-reduce on the communication
+            // stream is the barrier "every rank's stores are done".  The arena halves alternate, and
+            // every call ends with the compute stream waiting for the barrier, so a sender can only
+            // overwrite a half after its previous readers have finished.
+            // The exchange is cut in rounds (windows of `chunk` bytes of every segment): round k's
+            // unpack kernels (auxiliary stream) overlap the pack kernels of the later rounds
+            // (compute stream); the pack kernels run on a reduced grid because NVLink, not HBM,
+            // bounds them, which leaves SM resources for the kernels on the auxiliary stream.
+            const int64_t chunk = std::max<int64_t>(args.chunk_bytes, 1);
+            auto round_of = [&](const BoxOp &op) {
+                const int64_t off = (op.kind == BoxOp::Pack ? op.doff : op.soff) * esw;
+                return args.chunk_bytes > 0 ? (int)(off / chunk) : 0;
+            };
+            // all ranks run the same number of barriers: the round count comes from the largest
+            // message of the whole exchange
+            const int nrounds = args.chunk_bytes > 0
+                                    ? (int)std::max<int64_t>(1, (plan.max_pair_elems * esw + chunk - 1) / chunk)
+                                    : 1;
+            static int pack_grid = -1;
+            if (pack_grid < 0) {
+                const char *e = std::getenv("SBB_P2P_PACK_GRID");
+                pack_grid = e ? std::atoi(e) : 74; // measured best on 2 and 4 GPUs (24..296 tried)
+            }
+            std::vector<cudaEvent_t> &evs = round_events(home, 2 * nrounds);
+            use_device(home);
+            cuda_check(cudaEventRecord(hs.ev_a, hs.stream), "cudaEventRecord");
+            cuda_check(cudaStreamWaitEvent(hs.aux_stream, hs.ev_a, 0), "cudaStreamWaitEvent");
+            use_aux = true;
+            if (!args.add)
+                for (const auto &op : plan.ops)
+                    if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
+            for (int k = 0; k < nrounds; ++k) {
+                set_grid_cap(pack_grid);
+                for (const auto &op : plan.ops)
+                    if (op.kind == BoxOp::Pack && round_of(op) == k) run(op);
+                set_grid_cap(0);
+                use_device(home);
+                cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
+                cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
+                nccl_check(nccl().AllReduce(comm->flag, comm->flag + 8, 1, kNcclInt32, kNcclSum,
+                                            comm->nccl, hs.comm_stream),
+                           "ncclAllReduce (barrier)");
+                cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
+            }
+            auto wait_round = [&](int k) {
+                for (int a : devs) {
+                    use_device(a);
+                    cuda_check(cudaStreamWaitEvent(stream_for(a), evs[2 * k + 1], 0), "cudaStreamWaitEvent");
+                }
+            };
+            if (args.add) {
+                for (int k = 0; k < nrounds; ++k) wait_round(k);
+                for (const auto &op : plan.ops)
+                    if (op.kind != BoxOp::Pack) run(op);
+            } else {
+                for (int k = 0; k < nrounds; ++k) {
+                    wait_round(k);
+                    for (const auto &op : plan.ops)
+                        if (op.kind == BoxOp::Unpack && round_of(op) == k) run(op);
+                }
+            }
+            // the compute stream continues after everything of this call (also what makes the
+            // alternation of the arena halves safe)
+            use_device(home);
+            cuda_check(cudaEventRecord(hs.ev_c, hs.aux_stream), "cudaEventRecord");
+            cuda_check(cudaStreamWaitEvent(hs.stream, hs.ev_c, 0), "cudaStreamWaitEvent");
+            cuda_check(cudaStreamWaitEvent(hs.stream, evs[2 * nrounds - 1], 0), "cudaStreamWaitEvent");
+            use_aux = false;
+        } else if (plan.needs_comm) {
             // leave room for NCCL's kernels next to ours (SBB_COMM_GRID: CTAs of the copy kernels
             // while an exchange is in flight; 0 = no limit)
             static int comm_grid = -1;

@@ -15,7 +15,8 @@ namespace sbb {
         int id = -1;
         cudaStream_t stream = nullptr;      ///< all kernels of the library for this device
         cudaStream_t comm_stream = nullptr; ///< NCCL traffic, overlapped with `stream`
-        cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+        cudaStream_t aux_stream = nullptr;  ///< unpack / local kernels that overlap the pack kernels of an exchange
+        cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
     };
 
     DeviceState &device_state(int device);
@@ -33,6 +34,15 @@ namespace sbb {
     struct Comm {
         void *nccl = nullptr; ///< ncclComm_t
         int nranks = 1, rank = 0, device = 0;
+        // Peer-memory transport: every rank owns a receive arena (two halves, used alternately) that
+        // all other ranks map with CUDA IPC; pack kernels store straight into the receiver's arena
+        // over NVLink and one small NCCL all-reduce per exchange is the barrier.
+        bool p2p = false;          ///< transport usable (decided collectively at creation)
+        char *arena = nullptr;     ///< my arena
+        size_t half_bytes = 0;     ///< size of one half
+        std::vector<char *> peer;  ///< every rank's arena as mapped here (peer[rank] == arena)
+        unsigned long long epoch = 0;
+        int *flag = nullptr;       ///< device scratch for the barrier / handle exchange
     };
 
     void nccl_unique_id(void *id128);
