@@ -44,6 +44,8 @@ namespace sbb {
         struct ContractParams {
             Group T, M, N, K;
             int conj0, conj1;
+            int bn; // columns of an output tile of the mma kernel
+            int debug; // experiments only (SBB_MMA_DEBUG): 1 = no global loads in the main loop, 2 = also no barrier, 4 = no fragment loads
             // mma kernel
             int mtiles, ntiles, ksplit, ksteps; // ksteps = ceil(K/BK)
             int a_sr, a_sk, b_sr, b_sk;         // shared-memory strides (elements) of the operand tiles
@@ -152,7 +154,8 @@ namespace sbb {
 
         // ---- FP64 tensor-core kernel -----------------------------------------------------------------
 
-        constexpr int BM = 64, BN = 64, BK = 8, STAGES = 4, MMA_THREADS = 128;
+        constexpr int BM = 64, MMA_THREADS = 128;
+        // BN (tile columns), pipeline depth and resident CTAs are template parameters: 64/4/2 and 32/4/3 are built
 
         __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b) {
             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -172,6 +175,38 @@ namespace sbb {
             asm volatile("cp.async.wait_group %0;" ::"n"(N));
         }
 
+        // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ------------------
+        __device__ __forceinline__ unsigned smem_u32(const void *p) {
+            return (unsigned)__cvta_generic_to_shared(p);
+        }
+        __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+        }
+        __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                         "r"(bytes)
+                         : "memory");
+        }
+        __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+            asm volatile("{\n\t"
+                         ".reg .pred p;\n\t"
+                         "WAIT_%=:\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                         "@p bra DONE_%=;\n\t"
+                         "bra WAIT_%=;\n\t"
+                         "DONE_%=:\n\t"
+                         "}" ::"r"(smem_u32(bar)),
+                         "r"(parity)
+                         : "memory");
+        }
+        __device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes,
+                                                  unsigned long long *bar) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                             "r"(smem_u32(dst)),
+                         "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                         : "memory");
+        }
+
         template <typename T> struct Frag; // fragment element as loaded from shared memory
         template <> struct Frag<double> {
             static constexpr bool cplx = false;
@@ -187,12 +222,13 @@ namespace sbb {
             return group_offset(K, k, stride);
         }
 
-        template <typename T>
-        __global__ void __launch_bounds__(MMA_THREADS, 2)
+        template <typename T, int BN, int BK, int STAGES, int MINB, bool BULK>
+        __global__ void __launch_bounds__(MMA_THREADS, MINB)
             contract_mma_kernel(const __grid_constant__ ContractParams p, const T *__restrict__ v0,
                                 const T *__restrict__ v1, T *__restrict__ ws) {
             constexpr bool CPLX = Frag<T>::cplx;
             constexpr int ACC = CPLX ? 4 : 2; // doubles per 8x8 block per lane
+            constexpr int WN = BN / 16;       // 8-column blocks per warp (warp tile = 32 x BN/2)
             extern __shared__ __align__(16) unsigned char smem_raw[];
             // stage layout: [A tile | B tile], sizes fixed by the host (a_stage, b_stage elements)
             const int a_stage = p.a_kfast ? BM * p.a_sr : BK * p.a_sk;
@@ -201,7 +237,7 @@ namespace sbb {
             const int stage_elems = a_stage + b_stage;
 
             const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-            const int wm = warp >> 1, wn = warp & 1; // 2x2 warps, 32x32 each
+            const int wm = warp >> 1, wn = warp & 1; // 2x2 warps, 32 x BN/2 each
 
             // ---- which tile / K slice ------------------------------------------------------------
             long long bid = blockIdx.x;
@@ -241,9 +277,37 @@ namespace sbb {
                 b_sm[i] = a_stage + r * p.b_sr + kk * p.b_sk;
             }
 
+            // When the contracted labels merge into one dimension (the common case) every slot walks
+            // its row with a constant pointer increment; otherwise the K offset is decomposed per load.
+            const bool k_linear = p.K.n <= 1;
+            const T *a_ptr[A_SLOTS], *b_ptr[B_SLOTS];
+            const long long a_step = (p.K.n ? p.K.s0[0] : 0) * BK, b_step = (p.K.n ? p.K.s1[0] : 0) * BK;
+#pragma unroll
+            for (int i = 0; i < A_SLOTS; ++i)
+                a_ptr[i] = a_base + a_row[i] + ((long long)kstep0 * BK + a_kk[i]) * (p.K.n ? p.K.s0[0] : 0);
+#pragma unroll
+            for (int i = 0; i < B_SLOTS; ++i)
+                b_ptr[i] = b_base + b_row[i] + ((long long)kstep0 * BK + b_kk[i]) * (p.K.n ? p.K.s1[0] : 0);
             auto load_stage = [&](int stage, int kstep) {
                 T *s = smem + (size_t)stage * stage_elems;
                 const long long kbase = (long long)kstep * BK;
+                if (k_linear) {
+                    // stages are loaded in k order, so the pointers simply advance
+                    const bool tail = kbase + BK > p.K.vol;
+#pragma unroll
+                    for (int i = 0; i < A_SLOTS; ++i) {
+                        const bool ok = !tail || kbase + a_kk[i] < p.K.vol;
+                        cp_async<sizeof(T)>(s + a_sm[i], ok ? a_ptr[i] : a_base, ok);
+                        a_ptr[i] += a_step;
+                    }
+#pragma unroll
+                    for (int i = 0; i < B_SLOTS; ++i) {
+                        const bool ok = !tail || kbase + b_kk[i] < p.K.vol;
+                        cp_async<sizeof(T)>(s + b_sm[i], ok ? b_ptr[i] : b_base, ok);
+                        b_ptr[i] += b_step;
+                    }
+                    return;
+                }
 #pragma unroll
                 for (int i = 0; i < A_SLOTS; ++i) {
                     const long long k = kbase + a_kk[i];
@@ -260,76 +324,148 @@ namespace sbb {
                 }
             };
 
+            // TMA variant of the loader (operands whose tile rows are contiguous in memory): one
+            // cp.async.bulk per tile row instead of one cp.async per element; completion is
+            // tracked by one mbarrier per stage.  k-contiguous operand: BM (BN) copies of BK elements;
+            // row-contiguous operand: BK copies of BM (BN) elements.
+            __shared__ __align__(8) unsigned long long full_bar[STAGES];
+            long long bulk_off = 0; // source offset (elements) of this thread's copy at k = 0
+            int bulk_dst = 0;       // shared-memory position (elements) of this thread's copy
+            unsigned bulk_bytes = 0;
+            long long bulk_kstride = 0;
+            const T *bulk_base = a_base;
+            if (BULK) {
+                if (tid == 0) {
+#pragma unroll
+                    for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                }
+                __syncthreads();
+                const bool isA = tid < MMA_THREADS / 2;
+                const int c = isA ? tid : tid - MMA_THREADS / 2; // copy index inside the operand
+                const bool kfast = isA ? p.a_kfast : p.b_kfast;
+                const int rows = isA ? BM : BN;
+                const int ncopies = kfast ? rows : BK;
+                if (c < ncopies) {
+                    bulk_base = isA ? a_base : b_base;
+                    const long long kst = isA ? (p.K.n ? p.K.s0[0] : 0) : (p.K.n ? p.K.s1[0] : 0);
+                    if (kfast) {
+                        const long long r = min((long long)(isA ? mt * BM : nt * BN) + c,
+                                                (isA ? p.M.vol : p.N.vol) - 1);
+                        bulk_off = isA ? group_offset(p.M, r, p.M.s0) : group_offset(p.N, r, p.N.s1);
+                        bulk_dst = (isA ? 0 : a_stage) + c * (isA ? p.a_sr : p.b_sr);
+                        bulk_bytes = BK * sizeof(T);
+                        bulk_kstride = kst * BK; // per k-step
+                    } else {
+                        const long long r0 = (long long)(isA ? mt * BM : nt * BN);
+                        bulk_off = (isA ? group_offset(p.M, r0, p.M.s0) : group_offset(p.N, r0, p.N.s1)) +
+                                   c * kst;
+                        bulk_dst = (isA ? 0 : a_stage) + c * (isA ? p.a_sk : p.b_sk);
+                        bulk_bytes = rows * sizeof(T);
+                        bulk_kstride = kst * BK;
+                    }
+                }
+            }
+            auto load_stage_bulk = [&](int stage, int kstep) {
+                if (tid == 0)
+                    mbar_expect_tx(&full_bar[stage], (unsigned)((BM + BN) * BK * sizeof(T)));
+                if (bulk_bytes)
+                    bulk_load(smem + (size_t)stage * stage_elems + bulk_dst,
+                              bulk_base + bulk_off + (long long)kstep * bulk_kstride, bulk_bytes,
+                              &full_bar[stage]);
+            };
+
             // ---- accumulators: 4x4 blocks of 8x8 per warp ---------------------------------------------
-            double acc[4][4][ACC];
+            double acc[4][WN][ACC];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < WN; ++j)
 #pragma unroll
                     for (int c = 0; c < ACC; ++c) acc[i][j][c] = 0.0;
 
             // fragment addresses inside a stage: element (row = base + lane/4, k = lane%4)
-            int a_frag[4], b_frag[4];
+            int a_frag[4], b_frag[WN];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 4; ++i)
                 a_frag[i] = (wm * 32 + i * 8 + (lane >> 2)) * p.a_sr + (lane & 3) * p.a_sk;
-                b_frag[i] = a_stage + (wn * 32 + i * 8 + (lane >> 2)) * p.b_sr + (lane & 3) * p.b_sk;
-            }
+#pragma unroll
+            for (int j = 0; j < WN; ++j)
+                b_frag[j] = a_stage + (wn * (BN / 2) + j * 8 + (lane >> 2)) * p.b_sr + (lane & 3) * p.b_sk;
             const double sa = p.conj0 ? -1.0 : 1.0, sb = p.conj1 ? -1.0 : 1.0;
 
             // ---- pipeline -----------------------------------------------------------------------------
 #pragma unroll
             for (int s = 0; s < STAGES - 1; ++s) {
-                if (s < nsteps) load_stage(s, kstep0 + s);
-                cp_async_commit();
+                if (s < nsteps) {
+                    if (BULK) load_stage_bulk(s, kstep0 + s);
+                    else load_stage(s, kstep0 + s);
+                }
+                if (!BULK) cp_async_commit();
             }
             for (int it = 0; it < nsteps; ++it) {
-                cp_async_wait<STAGES - 2>();
-                __syncthreads();
-                {
-                    const int nxt = it + STAGES - 1;
-                    if (nxt < nsteps) load_stage(nxt % STAGES, kstep0 + nxt);
-                    cp_async_commit();
-                }
+                if (BULK) mbar_wait(&full_bar[it % STAGES], (unsigned)((it / STAGES) & 1));
+                else cp_async_wait<STAGES - 2>();
+                if (!(p.debug & 2)) __syncthreads();
                 const T *s = smem + (size_t)(it % STAGES) * stage_elems;
 #pragma unroll
                 for (int k4 = 0; k4 < BK / 4; ++k4) {
+                    if (k4 == (BK / 4 > 1 ? 1 : 0)) {
+                        // the next stage's loads are issued in the shadow of the first block of DMMAs
+                        // (the stage they overwrite was released by the barrier above)
+                        const int nxt = it + STAGES - 1;
+                        if (nxt < nsteps && !(p.debug & 1)) {
+                            if (BULK) load_stage_bulk(nxt % STAGES, kstep0 + nxt);
+                            else load_stage(nxt % STAGES, kstep0 + nxt);
+                        }
+                        if (!BULK) cp_async_commit();
+                    }
                     if constexpr (CPLX) {
-                        double ar[4], ai[4], nai[4], br[4], bi[4];
+                        double ar[4], ai[4], nai[4], br[WN], bi[WN];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const double2 a =
                                 *reinterpret_cast<const double2 *>(s + a_frag[i] + k4 * 4 * p.a_sk);
-                            const double2 b =
-                                *reinterpret_cast<const double2 *>(s + b_frag[i] + k4 * 4 * p.b_sk);
                             ar[i] = a.x, ai[i] = sa * a.y, nai[i] = -ai[i];
-                            br[i] = b.x, bi[i] = sb * b.y;
                         }
+#pragma unroll
+                        for (int j = 0; j < WN; ++j) {
+                            const double2 b =
+                                *reinterpret_cast<const double2 *>(s + b_frag[j] + k4 * 4 * p.b_sk);
+                            br[j] = b.x, bi[j] = sb * b.y;
+                        }
+                        // four passes over the 16 blocks: the two DMMAs that accumulate into the
+                        // same registers are 32 instructions apart, so none waits for the other
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
+                            for (int j = 0; j < WN; ++j) {
                                 dmma(acc[i][j][0], acc[i][j][1], ar[i], br[j]);
-                                dmma(acc[i][j][0], acc[i][j][1], nai[i], bi[j]);
                                 dmma(acc[i][j][2], acc[i][j][3], ar[i], bi[j]);
+                            }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < WN; ++j) {
+                                dmma(acc[i][j][0], acc[i][j][1], nai[i], bi[j]);
                                 dmma(acc[i][j][2], acc[i][j][3], ai[i], br[j]);
                             }
                     } else {
-                        double a[4], b[4];
+                        double a[4], b[WN];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < 4; ++i)
                             a[i] = *reinterpret_cast<const double *>(s + a_frag[i] + k4 * 4 * p.a_sk);
-                            b[i] = *reinterpret_cast<const double *>(s + b_frag[i] + k4 * 4 * p.b_sk);
-                        }
+#pragma unroll
+                        for (int j = 0; j < WN; ++j)
+                            b[j] = *reinterpret_cast<const double *>(s + b_frag[j] + k4 * 4 * p.b_sk);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                            for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
                     }
                 }
             }
-            cp_async_wait<0>();
+            if (!BULK) cp_async_wait<0>();
 
             // ---- partial tile to the workspace: ws[((t*mt*nt tile) * ksplit + ks)][m][n] -------------
             const long long tile_id = ((t * p.mtiles + mt) * p.ntiles + nt) * p.ksplit + ks;
@@ -337,9 +473,9 @@ namespace sbb {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < WN; ++j) {
                     const int row = wm * 32 + i * 8 + (lane >> 2);
-                    const int col = wn * 32 + j * 8 + (lane & 3) * 2;
+                    const int col = wn * (BN / 2) + j * 8 + (lane & 3) * 2;
                     if constexpr (CPLX) {
                         double4 v0 = make_double4(acc[i][j][0], acc[i][j][2], acc[i][j][1],
                                                   acc[i][j][3]);
@@ -361,6 +497,7 @@ namespace sbb {
                  idx += (long long)gridDim.x * blockDim.x) {
                 const long long n = idx % p.N.vol, m = (idx / p.N.vol) % p.M.vol,
                                 t = idx / (p.N.vol * p.M.vol);
+                const int BN = p.bn;
                 const int mt = (int)(m / BM), nt = (int)(n / BN);
                 const long long tile0 = ((t * p.mtiles + mt) * p.ntiles + nt) * p.ksplit;
                 const T *src = ws + tile0 * (long long)(BM * BN) + (m % BM) * BN + (n % BN);
@@ -446,9 +583,9 @@ namespace sbb {
         /// Shared-memory layout of an operand tile: k-contiguous operands are stored [row][k] with
         /// row stride = BK + pad, row-contiguous operands [k][row]; the pads make the fragment
         /// LDS conflict free (see the derivation in DESIGN.md).
-        void tile_layout(bool kfast, int esize, int rows, int &sr, int &sk) {
+        void tile_layout(bool kfast, int esize, int rows, int bk, int &sr, int &sk) {
             if (kfast) {
-                sr = BK + 4; // 12: = 4 mod 8 (16 B elements) and in {4,12} mod 16 (8 B elements)
+                sr = bk + 4; // 12: = 4 mod 8 (16 B elements) and in {4,12} mod 16 (8 B elements)
                 sk = 1;
             } else {
                 sk = rows + (esize == 16 ? 2 : 4);
@@ -456,25 +593,30 @@ namespace sbb {
             }
         }
 
-        template <typename T>
+        template <typename T, int BN, int BK, int STAGES, int MINB, bool BULK>
         void launch_mma(ContractParams p, const double *alpha, const void *v0, const void *v1,
                         const double *beta, void *vr, int device, cudaStream_t stream,
                         std::string *describe) {
+            p.bn = BN;
+            {
+                const char *e = std::getenv("SBB_MMA_DEBUG");
+                p.debug = e ? std::atoi(e) : 0;
+            }
             p.mtiles = (int)((p.M.vol + BM - 1) / BM);
             p.ntiles = (int)((p.N.vol + BN - 1) / BN);
             p.ksteps = (int)((p.K.vol + BK - 1) / BK);
             // operand enumeration: follow the contiguous direction in global memory
             p.a_kfast = p.K.n > 0 && (p.M.n == 0 || p.K.s0[0] <= p.M.s0[0]);
             p.b_kfast = p.K.n > 0 && (p.N.n == 0 || p.K.s1[0] <= p.N.s1[0]);
-            tile_layout(p.a_kfast, sizeof(T), BM, p.a_sr, p.a_sk);
-            tile_layout(p.b_kfast, sizeof(T), BN, p.b_sr, p.b_sk);
+            tile_layout(p.a_kfast, sizeof(T), BM, BK, p.a_sr, p.a_sk);
+            tile_layout(p.b_kfast, sizeof(T), BN, BK, p.b_sr, p.b_sk);
             const int a_stage = p.a_kfast ? BM * p.a_sr : BK * p.a_sk;
             const int b_stage = p.b_kfast ? BN * p.b_sr : BK * p.b_sk;
             const size_t smem = (size_t)(a_stage + b_stage) * STAGES * sizeof(T);
 
             // K split: fill the machine for several waves, keep every slice long
             const long long tiles = p.T.vol * p.mtiles * p.ntiles;
-            const long long slots = (long long)sm_count(device) * 2;
+            const long long slots = (long long)sm_count(device) * MINB;
             int best = 1;
             double best_eff = -1;
             const int smax = std::max(1, p.ksteps / 32);
@@ -494,22 +636,22 @@ namespace sbb {
                 ss << "mma f64 tile=" << BM << "x" << BN << "x" << BK << " stages=" << STAGES
                    << " T=" << p.T.vol << " M=" << p.M.vol << " N=" << p.N.vol << " K=" << p.K.vol
                    << " ksplit=" << p.ksplit << " ctas=" << ctas << " smem=" << smem
-                   << " a_kfast=" << p.a_kfast << " b_kfast=" << p.b_kfast;
+                   << " a_kfast=" << p.a_kfast << " b_kfast=" << p.b_kfast << " loader=" << (BULK ? "tma-bulk" : "cp.async");
                 *describe = ss.str();
                 return;
             }
             const size_t ws_bytes = (size_t)ctas * BM * BN * sizeof(T);
             T *ws = (T *)pool_alloc(device, ws_bytes);
-            static bool attr_set[64] = {false};
-            if (!attr_set[device]) {
-                cuda_check(cudaFuncSetAttribute(contract_mma_kernel<T>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024),
+            static size_t attr_smem[64] = {0};
+            if (smem > attr_smem[device]) {
+                cuda_check(cudaFuncSetAttribute(contract_mma_kernel<T, BN, BK, STAGES, MINB, BULK>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                            "cudaFuncSetAttribute");
-                attr_set[device] = true;
+                attr_smem[device] = smem;
             }
             {
                 KernelTimer timer("contract_mma", stream);
-                contract_mma_kernel<T><<<(unsigned)ctas, MMA_THREADS, smem, stream>>>(
+                contract_mma_kernel<T, BN, BK, STAGES, MINB, BULK><<<(unsigned)ctas, MMA_THREADS, smem, stream>>>(
                     p, (const T *)v0, (const T *)v1, ws);
             }
             count_launch();
@@ -552,10 +694,53 @@ namespace sbb {
         if (force && std::strcmp(force, "simt") == 0) use_mma = false;
         if (force && std::strcmp(force, "mma") == 0 && f64 && p.K.vol > 0) use_mma = true;
         if (use_mma) {
-            if (dtype == SBB_F64)
-                launch_mma<double>(p, alpha, v0, v1, beta, vr, device, stream, describe);
-            else
-                launch_mma<double2>(p, alpha, v0, v1, beta, vr, device, stream, describe);
+            // tile shape: 64x64 (2 CTAs/SM) or 64x32 (3 CTAs/SM, more warps to hide latencies);
+            // SBB_MMA_BN overrides for experiments
+            static int bn_env = -1;
+            if (bn_env < 0) {
+                const char *e = std::getenv("SBB_MMA_BN");
+                bn_env = e ? std::atoi(e) : 0;
+            }
+            const int bn = bn_env ? bn_env : 64;
+            static int bk_env = -1;
+            if (bk_env < 0) {
+                const char *e = std::getenv("SBB_MMA_BK");
+                bk_env = e ? std::atoi(e) : 0;
+            }
+            const int bk = bk_env ? bk_env : 8;
+            // TMA row loader when every tile row is one contiguous, 16-byte aligned run
+            const int esz = dtype == SBB_F64 ? 8 : 16;
+            auto rows_ok = [&](const Group &R, const long long *rs, const long long *ks, bool isA) {
+                const bool kfast = p.K.n > 0 && (R.n == 0 || ks[0] <= rs[0]);
+                if (kfast) return p.K.n == 1 && ks[0] == 1 && (8 * esz) % 16 == 0;
+                return R.n == 1 && rs[0] == 1 && R.vol % (isA ? BM : bn) == 0 && p.K.n <= 1;
+            };
+            static int bulk_env = -1;
+            if (bulk_env < 0) {
+                const char *e = std::getenv("SBB_MMA_BULK");
+                bulk_env = e ? std::atoi(e) : 0; // measured slower than per-element cp.async (27.6 vs 30.2 TFLOP/s): 128-byte bulk copies are too small
+            }
+            const bool bulk = bulk_env && !std::getenv("SBB_MMA_DEBUG") && bk == 8 && bn == 64 && p.K.vol % 8 == 0 &&
+                              rows_ok(p.M, p.M.s0, p.K.s0, true) && rows_ok(p.N, p.N.s1, p.K.s1, false) &&
+                              (uintptr_t)v0 % 16 == 0 && (uintptr_t)v1 % 16 == 0 &&
+                              [&] { // every other stride must keep 16-byte alignment too
+                                  if (esz == 16) return true;
+                                  for (const Group *g : {&p.T, &p.M, &p.N, &p.K})
+                                      for (int d = 0; d < g->n; ++d)
+                                          if ((g->s0[d] != 1 && g->s0[d] % 2) || (g->s1[d] != 1 && g->s1[d] % 2))
+                                              return false;
+                                  return true;
+                              }();
+#define SBB_MMA(T)                                                                                 \
+    do {                                                                                           \
+        if (bulk) launch_mma<T, 64, 8, 4, 2, true>(p, alpha, v0, v1, beta, vr, device, stream, describe); \
+        else if (bn == 32) launch_mma<T, 32, 8, 4, 3, false>(p, alpha, v0, v1, beta, vr, device, stream, describe);      \
+        else if (bk == 16) launch_mma<T, 64, 16, 2, 2, false>(p, alpha, v0, v1, beta, vr, device, stream, describe); \
+        else launch_mma<T, 64, 8, 4, 2, false>(p, alpha, v0, v1, beta, vr, device, stream, describe);      \
+    } while (0)
+            if (dtype == SBB_F64) SBB_MMA(double);
+            else SBB_MMA(double2);
+#undef SBB_MMA
             return;
         }
         if (describe) {

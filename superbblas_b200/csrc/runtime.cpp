@@ -112,7 +112,11 @@ namespace sbb {
                                          "CPU compute path; a B200 is required)");
             use_device(device);
             d.id = device;
-            cuda_check(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking), "stream");
+            // The compute stream is a *blocking* stream like the reference's (cudaStreamCreate,
+            // platform.h:304-309): it orders itself with the legacy default stream, so inputs produced
+            // there (thrust, torch's default stream, QDP-JIT) are seen without an explicit
+            // syncLegacyStream.  The communication and auxiliary streams are internal.
+            cuda_check(cudaStreamCreate(&d.stream), "stream");
             cuda_check(cudaStreamCreateWithFlags(&d.comm_stream, cudaStreamNonBlocking), "stream");
             cuda_check(cudaStreamCreateWithFlags(&d.aux_stream, cudaStreamNonBlocking), "stream");
             cuda_check(cudaEventCreateWithFlags(&d.ev_c, cudaEventDisableTiming), "event");
