@@ -25,6 +25,14 @@
 #ifndef SUPERBBLAS_B200_CXX_H
 #define SUPERBBLAS_B200_CXX_H
 
+// this build always has the GPU path (the reference defines these from its build flags, platform.h:76)
+#ifndef SUPERBBLAS_USE_CUDA
+#    define SUPERBBLAS_USE_CUDA
+#endif
+#ifndef SUPERBBLAS_USE_GPU
+#    define SUPERBBLAS_USE_GPU
+#endif
+
 #include "superbblas_b200.h"
 #include <algorithm>
 #include <array>
@@ -33,6 +41,7 @@
 #include <functional>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -55,11 +64,24 @@ namespace superbblas {
     const platform GPU = platform::CUDA;
 
     /// Where a component lives; same layout as sbb_context (and as the reference's Context)
+    namespace detail {
+        /// Low-level contexts of the reference (platform.h:173-217); here they only carry the Context
+        struct Cpu {
+            Session session = 0;
+        };
+        struct Gpu {
+            int device = 0;
+            Session session = 0;
+        };
+    }
+
     class Context {
     public:
         enum platform plat;
         int device;
         Context(enum platform plat, int device) : plat(plat), device(device) {}
+        detail::Cpu toCpu(Session session) const { return detail::Cpu{session}; }
+        detail::Gpu toGpu(Session session) const { return detail::Gpu{device, session}; }
     };
     static_assert(sizeof(Context) == sizeof(sbb_context), "Context must match sbb_context");
 
@@ -125,6 +147,86 @@ namespace superbblas {
         template <typename T> struct elem { using type = T; };
     }
 
+    // ---- detail:: helpers that the reference's own tests reach into (tests/contract.cpp:84-116,
+    //      tests/dist.cpp:93-97); kept source compatible so those tests compile unchanged -----------
+    namespace detail {
+        inline Context to_context(const Cpu &) { return Context{CPU, CPU_DEVICE_ID}; }
+        inline Context to_context(const Gpu &g) { return Context{CUDA, g.device}; }
+
+        /// Reference-counted buffer in the space of a context (reference: blas.h:240-358)
+        template <typename T, typename XPU> struct vector {
+            using T_no_const = typename std::remove_const<T>::type;
+            vector() : n(0), xpu() {}
+            vector(std::size_t n, XPU xpu) : n(n), xpu(xpu) {
+                Context c = to_context(xpu);
+                T_no_const *p = n ? superbblas_b200_alloc<T_no_const>(n, c) : nullptr;
+                ptr = std::shared_ptr<T_no_const>(p, [c](T_no_const *q) {
+                    if (q) sbb_deallocate(ctx_ptr(&c), (void *)q);
+                });
+            }
+            T *data() const { return ptr.get(); }
+            std::size_t size() const { return n; }
+            XPU ctx() const { return xpu; }
+
+        private:
+            template <typename U> static U *superbblas_b200_alloc(std::size_t n, Context c) {
+                void *p = nullptr;
+                check(sbb_allocate(ctx_ptr(&c), n * sizeof(U), &p));
+                return (U *)p;
+            }
+            std::size_t n;
+            std::shared_ptr<T_no_const> ptr;
+            XPU xpu;
+        };
+
+        /// Contiguous copy between contexts (reference: blas.h:170-231)
+        template <typename T, typename XPU0, typename XPU1>
+        void copy_n(const T *v, XPU0 xpu0, std::size_t n, T *w, XPU1 xpu1) {
+            Context c0 = to_context(xpu0), c1 = to_context(xpu1);
+            check(sbb_memcpy((void *)w, ctx_ptr(&c1), (const void *)v, ctx_ptr(&c0), n * sizeof(T)));
+        }
+
+        template <std::size_t N, typename I> Coor<N, I> operator+(const Coor<N, I> &a, const Coor<N, I> &b) {
+            Coor<N, I> r;
+            for (std::size_t i = 0; i < N; ++i) r[i] = a[i] + b[i];
+            return r;
+        }
+        template <std::size_t N, typename I> Coor<N, I> operator-(const Coor<N, I> &a, const Coor<N, I> &b) {
+            Coor<N, I> r;
+            for (std::size_t i = 0; i < N; ++i) r[i] = a[i] - b[i];
+            return r;
+        }
+
+        /// Jumps between consecutive coordinates (reference: tensor.h:282)
+        template <typename SIdx, std::size_t Nd, typename CIdx>
+        Coor<Nd, SIdx> get_strides(const Coor<Nd, CIdx> dim, CoorOrder co) {
+            Coor<Nd, SIdx> p;
+            if (Nd > 0) {
+                if (co == SlowToFast) {
+                    p[Nd - 1] = 1;
+                    for (std::size_t i = Nd - 1; i >= 1; --i) p[i - 1] = p[i] * dim[i];
+                } else {
+                    p[0] = 1;
+                    for (std::size_t i = 1; i < Nd; ++i) p[i] = p[i - 1] * dim[i - 1];
+                }
+            }
+            return p;
+        }
+        /// Linear index of a coordinate / coordinate of an index (reference: tensor.h:304, :334)
+        template <std::size_t Nd, typename CIdx, typename SIdx>
+        SIdx coor2index(const Coor<Nd, CIdx> &coor, const Coor<Nd, CIdx> &dim, const Coor<Nd, SIdx> &stride) {
+            SIdx r = 0;
+            for (std::size_t j = 0; j < Nd; ++j) r += (coor[j] % dim[j]) * stride[j];
+            return r;
+        }
+        template <std::size_t Nd, typename CIdx, typename SIdx>
+        Coor<Nd, CIdx> index2coor(const SIdx &index, const Coor<Nd, CIdx> &dim, const Coor<Nd, SIdx> &stride) {
+            Coor<Nd, CIdx> r;
+            for (std::size_t j = 0; j < Nd; ++j) r[j] = (CIdx)((index / stride[j]) % (SIdx)dim[j]);
+            return r;
+        }
+    }
+
     inline unsigned int getGpuDevicesCount() {
         int n = 0;
         detail::check(sbb_device_count(&n));
@@ -135,6 +237,16 @@ namespace superbblas {
     inline void sync(Context ctx) { detail::check(sbb_sync(detail::ctx_ptr(&ctx))); }
     inline void syncLegacyStream(Context ctx) {
         detail::check(sbb_sync_legacy_stream(detail::ctx_ptr(&ctx)));
+    }
+
+    /// Allocate / free memory in the space of a context (reference: alloc.h:398-425)
+    template <typename T> T *allocate(std::size_t n, Context ctx) {
+        void *p = nullptr;
+        detail::check(sbb_allocate(detail::ctx_ptr(&ctx), n * sizeof(T), &p));
+        return (T *)p;
+    }
+    template <typename T> void deallocate(T *ptr, Context ctx) {
+        detail::check(sbb_deallocate(detail::ctx_ptr(&ctx), (void *)ptr));
     }
 
     // Diagnostics of the reference that callers and its tests reference; cheap no-ops here

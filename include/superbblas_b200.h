@@ -63,6 +63,14 @@ int sbb_get_stream(int device, void **stream);
 /* Number of CUDA kernels launched by the library since the last call with reset != 0 */
 int sbb_launch_count(int reset, long long *count);
 
+/* allocate / deallocate (alloc.h:398-425): memory in the context's space (pooled device memory or
+ * 64-byte aligned host memory).  sbb_memcpy copies bytes between two contexts in stream order of the
+ * library stream; it returns when host destinations are complete. */
+int sbb_allocate(const sbb_context *ctx, size_t bytes, void **ptr);
+int sbb_deallocate(const sbb_context *ctx, void *ptr);
+int sbb_memcpy(void *dst, const sbb_context *dst_ctx, const void *src, const sbb_context *src_ctx,
+               size_t bytes);
+
 /* Device-side timing of the library's own kernels: when enabled every launch of the copy kernel
  * ("permute") and of the tensor-core contraction kernel ("contract_mma") is bracketed by CUDA events
  * on its stream; sbb_profile_read synchronises, returns the summed duration and clears the list. */

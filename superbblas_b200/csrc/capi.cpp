@@ -1,6 +1,7 @@
 // extern "C" entry points (include/superbblas_b200.h). Nothing here throws across the boundary.
 #include "contract_plan.hpp"
 #include "runtime.hpp"
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -131,6 +132,49 @@ int sbb_clear_handles(void) { SBB_TRY(destroy_all_streams()); }
 int sbb_get_stream(int device, void **stream) { SBB_TRY(*stream = device_state(device).stream); }
 
 int sbb_launch_count(int reset, long long *count) { SBB_TRY(*count = launch_count(reset != 0)); }
+
+int sbb_allocate(const sbb_context *ctx, size_t bytes, void **ptr) {
+    SBB_TRY({
+        *ptr = nullptr;
+        if (ctx->plat == SBB_CPU) {
+            // pageable, 64-byte aligned (pinning is the caller's choice: it costs ~1 ms per call)
+            if (posix_memalign(ptr, 64, bytes ? bytes : 64) != 0) throw std::runtime_error("out of memory");
+        } else if (ctx->plat == SBB_CUDA) {
+            device_state(ctx->device);
+            *ptr = pool_alloc(ctx->device, bytes);
+        } else {
+            throw std::runtime_error("Unsupported platform");
+        }
+    });
+}
+
+int sbb_deallocate(const sbb_context *ctx, void *ptr) {
+    SBB_TRY({
+        if (!ptr) return 0;
+        if (ctx->plat == SBB_CPU) {
+            std::free(ptr);
+        } else {
+            pool_free(ctx->device, ptr);
+        }
+    });
+}
+
+int sbb_memcpy(void *dst, const sbb_context *dst_ctx, const void *src, const sbb_context *src_ctx,
+               size_t bytes) {
+    SBB_TRY({
+        if (bytes == 0) return 0;
+        const bool dh = dst_ctx->plat == SBB_CPU, sh = src_ctx->plat == SBB_CPU;
+        if (dh && sh) {
+            std::memcpy(dst, src, bytes);
+            return 0;
+        }
+        const int dev = dh ? src_ctx->device : dst_ctx->device;
+        DeviceState &d = device_state(dev);
+        use_device(dev);
+        cuda_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, d.stream), "cudaMemcpyAsync");
+        if (dh) cuda_check(cudaStreamSynchronize(d.stream), "cudaStreamSynchronize");
+    });
+}
 
 int sbb_profile_enable(int on) { SBB_TRY(profile_enable(on != 0)); }
 

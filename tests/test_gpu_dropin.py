@@ -17,3 +17,27 @@ def test_cxx_dropin_program():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Everything went ok!" in r.stdout
+
+
+def _run_reference_suite(args, timeout=900):
+    exe = os.path.join(HERE, "cxx", "ref_contract_wrapper")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cxx/ref_contract_wrapper not built (needs /root/reference at build time)")
+    r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    assert "Everything went ok!" in r.stdout
+
+
+@pytest.mark.parametrize("nt", [0, 1])
+@pytest.mark.parametrize("typ", ["d", "z"])
+def test_reference_own_contraction_suite(nt, typ):
+    """The reference's tests/contract.cpp, unmodified (included from /root/reference at build time
+    by tests/cxx/ref_contract_wrapper.cpp), compiled against include/superbblas.h and run on the GPU:
+    every label-group arrangement, order, conjugation, alpha/beta and partition of its enumeration
+    (1.3 million contractions over the four parametrisations)."""
+    _run_reference_suite(["--nt=%d" % nt, "--type=%s" % typ])
+
+
+# The wrapper also accepts --components=N (several components per process) and --cpu (host contexts,
+# staged through the GPU); they run the same enumeration but take much longer, so they are not part of
+# the default GPU test run.
