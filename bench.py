@@ -77,6 +77,30 @@ def cpu_contraction_sample(reps, warmup):
                        "OMP_NUM_THREADS=%d OPENBLAS_NUM_THREADS=1" % (CPU_SAMPLE_T, flop, cores))
 
 
+def cpu_copy_sample(reps=5):
+    """The reference's CPU copy on a bounded sample of the reshuffle workload: "xyztsc" -> "cstzyx" on
+    16^3 x 32 x 4 x 3 complex double (25 MB; warm calls, i.e. with its index vectors cached)."""
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    from oracle import ref as R
+    dim0, dim1 = [16, 16, 16, 32, 4, 3], [3, 4, 32, 16, 16, 16]
+    p0 = np.array([[[0] * 6, dim0]], dtype=np.int32)
+    p1 = np.array([[[0] * 6, dim1]], dtype=np.int32)
+    n = int(np.prod(dim0))
+    rng = np.random.default_rng(1)
+    a = rng.random(n) + 1j * rng.random(n)
+    b = np.zeros(n, dtype=np.complex128)
+    best = None
+    for i in range(reps + 2):
+        t0 = time.perf_counter()
+        R.copy(1, p0, "xyztsc", [0] * 6, dim0, dim0, [a], p1, "cstzyx", [0] * 6, dim1, [b], "FastToSlow", 0)
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            best = dt if best is None else min(best, dt)
+    return {"GB/s": 2 * n * 16 / best / 1e9, "ms": best * 1e3, "cores": cores, "kind": "reference",
+            "sample": "16^3 x 32 x 4 x 3 complex double (25 MB), warm (index vectors cached)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -327,6 +351,13 @@ def main():
         torch.cuda.empty_cache()
         extras = reshuffle_extras(sb, torch, dist, dev, gpu, stream, comm, rank, world, timed,
                                   hbm_peak)
+
+    # ---- CPU reference for the reshuffle (rank 0, N=1 only): same permutation, 16^3 x 32 x 4 x 3 ------------
+    if world == 1 and not args.no_cpu and not args.no_extras:
+        try:
+            extras["cpu_reference_permute_xyztsc_cstzyx_c128"] = cpu_copy_sample()
+        except Exception as e:  # noqa: BLE001
+            extras["cpu_reference_permute_xyztsc_cstzyx_c128"] = {"unavailable": str(e)}
 
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
     cpu_baseline = None
