@@ -323,6 +323,26 @@ def main():
         got0 = r.view(NV, NV, LT)[:, :, 0]
         check_ok = bool((torch.linalg.norm(got0 - ref0) / torch.linalg.norm(ref0)).item() < 1e-12)
 
+    # ---- the same contraction on complex float operands (N=1): products and K sum on the FP64 tensor pipe ---
+    contraction_c64 = None
+    if world == 1 and not args.no_extras:
+        af, bf = a.to(torch.complex64), b.to(torch.complex64)
+        rf = torch.zeros(nout, device=dev, dtype=torch.complex64)
+        sb.profile_enable(True)
+        sb.profile_read("contract_mma")
+        ms_f = timed(lambda: step(af, bf, rf, gpu), 10, 3)
+        kms_f, kn_f = sb.profile_read("contract_mma")
+        sb.profile_enable(False)
+        ref0f = (B0 @ A0.conj().T)
+        got0f = rf.view(NV, NV, LT)[:, :, 0].to(torch.complex128)
+        contraction_c64 = {"TFLOP/s": FLOP_PER_GPU * 10 / (ms_f * 1e-3) / 1e12, "ms": ms_f / 10,
+                           "kernel_ms": kms_f / max(kn_f, 1),
+                           "frac_of_fp64_tensor_peak": FLOP_PER_GPU / (kms_f / max(kn_f, 1) * 1e-3) / 1e12 / fp64_peak,
+                           "rel_err_vs_c128": float((torch.linalg.norm(got0f - ref0f) /
+                                                     torch.linalg.norm(ref0f)).item()),
+                           "min_bytes": 2 * nloc * 8 + nout * 8}
+        del af, bf, rf
+
     # ---- e2e: HOST operands in pinned memory through the same public call ---------------------------------
     e2e_steps = max(1, min(args.steps, 3))
     ha = torch.empty(nloc, dtype=torch.complex128, pin_memory=True)
@@ -393,7 +413,8 @@ def main():
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "result_check": check_ok,
-            "reshuffle": extras, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
+            "reshuffle": extras, "contraction_c64": contraction_c64, "hbm_peak_gbs": hbm_peak,
+            "hbm_peak_source": hbm_src,
         }
         print(json.dumps(line))
     if world > 1:
@@ -435,6 +456,18 @@ def reshuffle_extras(sb, torch, dist, dev, gpu, stream, comm, rank, world, timed
     record("permute_xyztsc_cstzyx_c128", 2 * n * 16,
            lambda: sb.copy(1, p0, 1, "xyztsc", [0] * 6, dim0, dim0, [x], None, gpu, p1, 1, "cstzyx",
                            [0] * 6, dim1, [y], None, gpu, sb.FastToSlow, sb.Copy))
+    if world == 1:
+        # (a') the same permutation restricted to the even sites by MaskType masks on both tensors (§8f row 1);
+        # bytes as the reference counts them for masked copies: mask size x (sizeof T + sizeof Q), tensor.h:1087
+        idx = torch.arange(n, device=dev)
+        par = (idx % 32 + (idx // 32) % 32 + (idx // 1024) % 32 + (idx // 32768) % 64) % 2
+        m0 = (par == 0).to(torch.float32)
+        m1 = m0.view(3, 4, 64, 32, 32, 32).permute(5, 4, 3, 2, 1, 0).contiguous().view(-1)
+        del idx, par
+        record("masked_even_sites_permute_xyztsc_cstzyx_c128", 2 * n * 16,
+               lambda: sb.copy(1, p0, 1, "xyztsc", [0] * 6, dim0, dim0, [x], [m0], gpu, p1, 1, "cstzyx",
+                               [0] * 6, dim1, [y], [m1], gpu, sb.FastToSlow, sb.Copy), steps=10)
+        del m0, m1
     del x, y
     # (b) periodic +1 shifts of a 64^3 x 128 x 4 x 3 field distributed on z,t (config 5): per GPU block
     pz, pt = grid_for(world)

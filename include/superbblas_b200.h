@@ -106,7 +106,14 @@ int sbb_make_hole(int nd, const int *from, const int *size, const int *hole_from
 /* v1[from1 + perm(c - from0)] (+)= Q(alpha * v0[c]) for c in [from0, from0+size0) (periodic).
  *   p0, p1 : partitions, int[nparts][2][nd] with nparts = nranks*ncomponents
  *   o0, o1 : label strings of length nd0, nd1
- *   v0, v1 : one pointer per LOCAL component; mask0/mask1 must be NULL (masks: not implemented)
+ *   v0, v1 : one pointer per LOCAL component
+ *   mask0, mask1 : NULL, or one MaskType (float) array per LOCAL component, laid out exactly like
+ *            the component and living in the same context (reference: Mask<XPU>, dist.h:169,
+ *            tensor.h:1022-1027).  An element moves iff mask0 is nonzero at its source and mask1
+ *            is nonzero at its destination; everything else in v1 is left untouched.  Replicated
+ *            source parts must carry consistent masks.  The reference only accepts "compatible"
+ *            pairs (mask1 = mask0 carried to the destination); for those the results are
+ *            identical.
  *   alpha  : {re, im} (im ignored for real T); the value is converted to T
  * The call is asynchronous with respect to GPU components (use sbb_sync); host (SBB_CPU) destination
  * components are complete on return. */

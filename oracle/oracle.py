@@ -153,6 +153,7 @@ def copy(alpha, p0, o0, from0, size0, dim0, v0, p1, o1, from1, dim1, v1, co, cop
             if int(np.prod(si)) == 0:
                 continue
             hit = _in_interval(fi, si, dim0, c0)
+            covered |= hit  # coverage is geometric (has_full_support, dist.h:666): masks do not uncover
             l0 = (c0[hit] - fi) % np.asarray(dim0, dtype=np.int64)
             src_idx = (l0 * np.asarray(strides0[i], dtype=np.int64)).sum(axis=1)
             if mask0 is not None and mask0[i] is not None:

@@ -60,14 +60,17 @@ def _ab(x):
     return a
 
 
-def copy(alpha, p0, o0, from0, size0, dim0, v0, p1, o1, from1, dim1, v1, co, copyadd):
+def copy(alpha, p0, o0, from0, size0, dim0, v0, p1, o1, from1, dim1, v1, co, copyadd,
+         mask0=None, mask1=None):
     k = []
     a = [_ia(x) for x in (p0, from0, size0, dim0, p1, from1, dim1)]
     k.extend(a)
-    _check(lib().sbref_copy(
+    m0 = _ptrs(mask0) if mask0 is not None else None
+    m1 = _ptrs(mask1) if mask1 is not None else None
+    _check(lib().sbref_copy_masked(
         DT[v0[0].dtype], DT[v1[0].dtype], _ab(alpha), len(o0), a[0][1], len(v0), o0.encode(),
-        a[1][1], a[2][1], a[3][1], _ptrs(v0), len(o1), a[4][1], len(v1), o1.encode(), a[5][1],
-        a[6][1], _ptrs(v1), _co(co), int(copyadd)))
+        a[1][1], a[2][1], a[3][1], _ptrs(v0), m0, len(o1), a[4][1], len(v1), o1.encode(), a[5][1],
+        a[6][1], _ptrs(v1), m1, _co(co), int(copyadd)))
 
 
 def contraction(alpha, p0, from0, size0, dim0, o0, conj0, v0, p1, from1, size1, dim1, o1, conj1,

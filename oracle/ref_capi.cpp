@@ -95,7 +95,7 @@ namespace {
     void do_copy(const double *alpha, int nd0, const int *p0, int ncomp0, const char *o0,
                  const int *from0, const int *size0, const int *dim0, const void **v0, int nd1,
                  const int *p1, int ncomp1, const char *o1, const int *from1, const int *dim1,
-                 void **v1, int co, int copyadd) {
+                 void **v1, int co, int copyadd, const float **mask0, const float **mask1) {
         std::vector<bool> used(128, false);
         mark(o0, used);
         mark(o1, used);
@@ -103,8 +103,8 @@ namespace {
         Padded t1 = pad(nd1, p1, ncomp1, o1, from1, nullptr, dim1, used);
         std::vector<Context> ctx0(ncomp0, createCpuContext()), ctx1(ncomp1, createCpuContext());
         copy<ND, ND, T, Q>(mk<T>(alpha), t0.p.data(), ncomp0, t0.o, t0.from, t0.size, t0.dim,
-                           (const T **)v0, nullptr, ctx0.data(), t1.p.data(), ncomp1, t1.o,
-                           t1.from, t1.dim, (Q **)v1, nullptr, ctx1.data(),
+                           (const T **)v0, mask0, ctx0.data(), t1.p.data(), ncomp1, t1.o,
+                           t1.from, t1.dim, (Q **)v1, mask1, ctx1.data(),
                            co == 0 ? SlowToFast : FastToSlow, copyadd == 0 ? Copy : Add);
     }
 
@@ -205,9 +205,10 @@ extern "C" {
 int SBREF_COPY_NAME(const double *alpha, int nd0, const int *p0, int ncomp0, const char *o0,
                     const int *from0, const int *size0, const int *dim0, const void **v0, int nd1,
                     const int *p1, int ncomp1, const char *o1, const int *from1, const int *dim1,
-                    void **v1, int co, int copyadd) {
+                    void **v1, int co, int copyadd, const float **mask0, const float **mask1) {
     SBREF_TRY((do_copy<SBREF_T, SBREF_Q>(alpha, nd0, p0, ncomp0, o0, from0, size0, dim0, v0, nd1,
-                                         p1, ncomp1, o1, from1, dim1, v1, co, copyadd)));
+                                         p1, ncomp1, o1, from1, dim1, v1, co, copyadd, mask0,
+                                         mask1)));
 }
 #endif
 
@@ -232,7 +233,7 @@ const char *sbref_last_error() { return g_err.c_str(); }
 #    define DECL_COPY(N)                                                                           \
         int N(const double *, int, const int *, int, const char *, const int *, const int *,      \
               const int *, const void **, int, const int *, int, const char *, const int *,       \
-              const int *, void **, int, int);
+              const int *, void **, int, int, const float **, const float **);
 DECL_COPY(sbref_copy_0_0)
 DECL_COPY(sbref_copy_1_1)
 DECL_COPY(sbref_copy_2_2)
@@ -253,19 +254,30 @@ DECL_CONTR(sbref_contraction_1)
 DECL_CONTR(sbref_contraction_2)
 DECL_CONTR(sbref_contraction_3)
 
-int sbref_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0, int ncomp0,
-               const char *o0, const int *from0, const int *size0, const int *dim0,
-               const void **v0, int nd1, const int *p1, int ncomp1, const char *o1,
-               const int *from1, const int *dim1, void **v1, int co, int copyadd) {
+/// mask0/mask1: NULL, or one MaskType (float) array per component, laid out like the component
+int sbref_copy_masked(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0,
+                      int ncomp0, const char *o0, const int *from0, const int *size0,
+                      const int *dim0, const void **v0, const float **mask0, int nd1,
+                      const int *p1, int ncomp1, const char *o1, const int *from1, const int *dim1,
+                      void **v1, const float **mask1, int co, int copyadd) {
 #    define CASE(A, B)                                                                             \
         if (dtype0 == A && dtype1 == B)                                                            \
             return sbref_copy_##A##_##B(alpha, nd0, p0, ncomp0, o0, from0, size0, dim0, v0, nd1,   \
-                                        p1, ncomp1, o1, from1, dim1, v1, co, copyadd);
+                                        p1, ncomp1, o1, from1, dim1, v1, co, copyadd, mask0,       \
+                                        mask1);
     CASE(0, 0) CASE(1, 1) CASE(2, 2) CASE(3, 3) CASE(4, 4) CASE(0, 1) CASE(1, 0) CASE(2, 3)
         CASE(3, 2)
 #    undef CASE
     g_err = "sbref_copy: unsupported type combination";
     return 1;
+}
+
+int sbref_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0, int ncomp0,
+               const char *o0, const int *from0, const int *size0, const int *dim0,
+               const void **v0, int nd1, const int *p1, int ncomp1, const char *o1,
+               const int *from1, const int *dim1, void **v1, int co, int copyadd) {
+    return sbref_copy_masked(dtype0, dtype1, alpha, nd0, p0, ncomp0, o0, from0, size0, dim0, v0,
+                             nullptr, nd1, p1, ncomp1, o1, from1, dim1, v1, nullptr, co, copyadd);
 }
 
 int sbref_contraction(int dtype, const double *alpha, int nd0, const int *p0, const int *from0,

@@ -247,19 +247,31 @@ def make_hole(frm, size, hole_from, hole_size, dim):
 def copy(alpha, p0, ncomponents0, o0, from0, size0, dim0, v0, mask0, ctx0,
          p1, ncomponents1, o1, from1, dim1, v1, mask1, ctx1, co, copyadd, comm=None):
     """superbblas::copy (dist.h:3583; with `comm` the MPI overload dist.h:3534)."""
-    if mask0 is not None or mask1 is not None:
-        raise RuntimeError("copy: masks are not implemented")
     n0, n1 = len(o0), len(o1)
     pv0, dt0, k0 = _components(v0)
     pv1, dt1, k1 = _components(v1)
     if len(v0) != ncomponents0 or len(v1) != ncomponents1:
         raise RuntimeError("wtf")
+    # masks (MaskType = float32, one per component, laid out like the component; nonzero = active)
+    pm0 = pm1 = None
+    if mask0 is not None:
+        if len(mask0) != ncomponents0:
+            raise RuntimeError("wtf")
+        pm0, mdt, km0 = _components(mask0)
+        if mdt != F32:
+            raise RuntimeError("masks must be float32 (MaskType)")
+    if mask1 is not None:
+        if len(mask1) != ncomponents1:
+            raise RuntimeError("wtf")
+        pm1, mdt, km1 = _components(mask1)
+        if mdt != F32:
+            raise RuntimeError("masks must be float32 (MaskType)")
     nr = comm.nranks if comm else 1
     a = [_partition(p0, nr * ncomponents0, n0), _ia(from0, n0), _ia(size0, n0), _ia(dim0, n0),
          _partition(p1, nr * ncomponents1, n1), _ia(from1, n1), _ia(dim1, n1)]
     check(lib().sbb_copy(dt0, dt1, _scalar(alpha), n0, _ip(a[0]), ncomponents0, _order(o0),
-                         _ip(a[1]), _ip(a[2]), _ip(a[3]), pv0, None, _contexts(ctx0, ncomponents0),
-                         n1, _ip(a[4]), ncomponents1, _order(o1), _ip(a[5]), _ip(a[6]), pv1, None,
+                         _ip(a[1]), _ip(a[2]), _ip(a[3]), pv0, pm0, _contexts(ctx0, ncomponents0),
+                         n1, _ip(a[4]), ncomponents1, _order(o1), _ip(a[5]), _ip(a[6]), pv1, pm1,
                          _contexts(ctx1, ncomponents1), comm.handle if comm else None, _co(co),
                          int(copyadd)))
 
@@ -270,8 +282,8 @@ def local_copy(alpha, o0, from0, size0, dim0, v0, mask0, ctx0, o1, from1, dim1, 
     n0, n1 = len(o0), len(o1)
     p0 = np.array([[[0] * n0, list(dim0)]], dtype=np.int32)
     p1 = np.array([[[0] * n1, list(dim1)]], dtype=np.int32)
-    copy(alpha, p0, 1, o0, from0, size0, dim0, [v0], mask0, [ctx0], p1, 1, o1, from1, dim1, [v1],
-         mask1, [ctx1], co, copyadd)
+    copy(alpha, p0, 1, o0, from0, size0, dim0, [v0], None if mask0 is None else [mask0], [ctx0],
+         p1, 1, o1, from1, dim1, [v1], None if mask1 is None else [mask1], [ctx1], co, copyadd)
 
 
 def copy_plan(elem_size1, p0, ncomponents0, o0, from0, size0, dim0, p1, ncomponents1, o1, from1,

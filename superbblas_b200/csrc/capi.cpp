@@ -240,10 +240,9 @@ int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0
              int co, int copyadd) {
     SBB_TRY({
         Comm *c = (Comm *)comm;
-        for (int i = 0; mask0 && i < ncomponents0; ++i)
-            if (mask0[i]) throw std::runtime_error("copy: masks are not implemented");
-        for (int i = 0; mask1 && i < ncomponents1; ++i)
-            if (mask1[i]) throw std::runtime_error("copy: masks are not implemented");
+        bool has_m0 = false, has_m1 = false;
+        for (int i = 0; mask0 && i < ncomponents0; ++i) has_m0 = has_m0 || mask0[i] != nullptr;
+        for (int i = 0; mask1 && i < ncomponents1; ++i) has_m1 = has_m1 || mask1[i] != nullptr;
         CopyArgs a = make_copy_args(nd0, p0, ncomponents0, o0, from0, size0, dim0, nd1, p1,
                                     ncomponents1, o1, from1, dim1, c ? c->nranks : 1,
                                     c ? c->rank : 0, co, copyadd);
@@ -252,8 +251,47 @@ int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0
         a.wire_align = 16 / dtype_bytes((a.add && dtype0 != dtype1) ? dtype0 : dtype1);
         a.chunk_bytes = exchange_chunk_bytes();
         auto plan = get_copy_plan(a);
-        execute_copy(*plan, a, dtype0, dtype1, alpha, buffers(v0, ctx0, ncomponents0),
-                     buffers((const void *const *)v1, ctx1, ncomponents1), c);
+        if (!has_m0 && !has_m1) {
+            execute_copy(*plan, a, dtype0, dtype1, alpha, buffers(v0, ctx0, ncomponents0),
+                         buffers((const void *const *)v1, ctx1, ncomponents1), c);
+            return 0;
+        }
+        // Masked copy (reference: tensor.h:1022-1027, dist.h:944-970, :1240-1243): an element moves
+        // iff the source mask at its origin and the destination mask at its target are nonzero.
+        // Step 1 carries mask0 to the destination layout with the copy engine itself (a float copy
+        // with the same geometry, exchange included); step 2 is the data copy with the two masks as
+        // a predicate on every destination store.
+        std::vector<Buffer> m0b, m1b, tmp;
+        if (has_m1) m1b = buffers((const void *const *)mask1, ctx1, ncomponents1);
+        if (has_m0 && !a.alpha_is_zero) {
+            m0b = buffers((const void *const *)mask0, ctx0, ncomponents0);
+            tmp.resize(ncomponents1);
+            for (int i = 0; i < ncomponents1; ++i) {
+                const int64_t vol = volume(a.p1[(size_t)a.rank * ncomponents1 + i].size);
+                const int dev = ctx1[i].plat == SBB_CUDA ? ctx1[i].device : default_device(c);
+                tmp[i].host = false, tmp[i].device = dev;
+                tmp[i].ptr = pool_alloc(dev, (size_t)std::max<int64_t>(vol, 1) * sizeof(float));
+            }
+            CopyArgs am = a;
+            am.add = false;
+            am.wire_align = 16 / (int)sizeof(float);
+            const double one[2] = {1, 0};
+            try {
+                execute_copy(*get_copy_plan(am), am, SBB_F32, SBB_F32, one, m0b, tmp, c);
+            } catch (...) {
+                for (auto &t : tmp) pool_free(t.device, t.ptr);
+                throw;
+            }
+        }
+        try {
+            execute_copy(*plan, a, dtype0, dtype1, alpha, buffers(v0, ctx0, ncomponents0),
+                         buffers((const void *const *)v1, ctx1, ncomponents1), c,
+                         tmp.empty() ? nullptr : &tmp, has_m1 ? &m1b : nullptr);
+        } catch (...) {
+            for (auto &t : tmp) pool_free(t.device, t.ptr);
+            throw;
+        }
+        for (auto &t : tmp) pool_free(t.device, t.ptr);
     });
 }
 

@@ -34,9 +34,12 @@ namespace sbb {
 
     /// dst (+)= Q(alpha*src) over a strided box. The current device must be `device`.
     /// If `describe` is given nothing is launched and the chosen variant is described instead.
+    /// mask_a / mask_b (optional, MaskType = float, laid out exactly like dst): an element of dst
+    /// is written only where every given mask is nonzero.
     void permute_copy(const sbk_box_desc &box, const void *src, int dtype_src, void *dst,
                       int dtype_dst, const double *alpha, bool add, int device, cudaStream_t stream,
-                      std::string *describe = nullptr);
+                      std::string *describe = nullptr, const float *mask_a = nullptr,
+                      const float *mask_b = nullptr);
 
     void set_grid_cap(int ctas);
     int grid_cap();

@@ -214,6 +214,15 @@ namespace sbb {
         template <> struct Frag<double2> {
             static constexpr bool cplx = true;
         };
+        // float and complex float operands stay in their own type up to shared memory (half the HBM
+        // and shared-memory traffic) and are widened when the fragments are read: the products and
+        // the whole K sum are done by the FP64 tensor pipe, only the final result is rounded to float
+        template <> struct Frag<float> {
+            static constexpr bool cplx = false;
+        };
+        template <> struct Frag<float2> {
+            static constexpr bool cplx = true;
+        };
 
         /// Offset of contracted index k in an operand
         __device__ __forceinline__ long long k_offset(const Group &K, long long k,
@@ -225,7 +234,8 @@ namespace sbb {
         template <typename T, int BN, int BK, int STAGES, int MINB, bool BULK>
         __global__ void __launch_bounds__(MMA_THREADS, MINB)
             contract_mma_kernel(const __grid_constant__ ContractParams p, const T *__restrict__ v0,
-                                const T *__restrict__ v1, T *__restrict__ ws) {
+                                const T *__restrict__ v1, typename Acc<T>::type *__restrict__ ws) {
+            using A = typename Acc<T>::type; // double or double2: what the partial tiles are stored as
             constexpr bool CPLX = Frag<T>::cplx;
             constexpr int ACC = CPLX ? 4 : 2; // doubles per 8x8 block per lane
             constexpr int WN = BN / 16;       // 8-column blocks per warp (warp tile = 32 x BN/2)
@@ -424,14 +434,12 @@ namespace sbb {
                         double ar[4], ai[4], nai[4], br[WN], bi[WN];
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const double2 a =
-                                *reinterpret_cast<const double2 *>(s + a_frag[i] + k4 * 4 * p.a_sk);
+                            const double2 a = widen(s[a_frag[i] + k4 * 4 * p.a_sk]);
                             ar[i] = a.x, ai[i] = sa * a.y, nai[i] = -ai[i];
                         }
 #pragma unroll
                         for (int j = 0; j < WN; ++j) {
-                            const double2 b =
-                                *reinterpret_cast<const double2 *>(s + b_frag[j] + k4 * 4 * p.b_sk);
+                            const double2 b = widen(s[b_frag[j] + k4 * 4 * p.b_sk]);
                             br[j] = b.x, bi[j] = sb * b.y;
                         }
                         // four passes over the 16 blocks: the two DMMAs that accumulate into the
@@ -454,10 +462,10 @@ namespace sbb {
                         double a[4], b[WN];
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            a[i] = *reinterpret_cast<const double *>(s + a_frag[i] + k4 * 4 * p.a_sk);
+                            a[i] = widen(s[a_frag[i] + k4 * 4 * p.a_sk]);
 #pragma unroll
                         for (int j = 0; j < WN; ++j)
-                            b[j] = *reinterpret_cast<const double *>(s + b_frag[j] + k4 * 4 * p.b_sk);
+                            b[j] = widen(s[b_frag[j] + k4 * 4 * p.b_sk]);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -469,7 +477,7 @@ namespace sbb {
 
             // ---- partial tile to the workspace: ws[((t*mt*nt tile) * ksplit + ks)][m][n] -------------
             const long long tile_id = ((t * p.mtiles + mt) * p.ntiles + nt) * p.ksplit + ks;
-            T *out = ws + tile_id * (long long)(BM * BN);
+            A *out = ws + tile_id * (long long)(BM * BN);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -490,8 +498,10 @@ namespace sbb {
         /// Sum the K-slices of every output tile in a fixed order and write alpha*sum + beta*vr
         template <typename T>
         __global__ void __launch_bounds__(256)
-            contract_reduce_kernel(const __grid_constant__ ContractParams p, const T *__restrict__ ws,
-                                   T *vr, T alpha, T beta) {
+            contract_reduce_kernel(const __grid_constant__ ContractParams p,
+                                   const typename Acc<T>::type *__restrict__ ws, T *vr,
+                                   typename Acc<T>::type alpha, typename Acc<T>::type beta) {
+            using A = typename Acc<T>::type;
             const long long total = p.T.vol * p.M.vol * p.N.vol;
             for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
                  idx += (long long)gridDim.x * blockDim.x) {
@@ -500,14 +510,14 @@ namespace sbb {
                 const int BN = p.bn;
                 const int mt = (int)(m / BM), nt = (int)(n / BN);
                 const long long tile0 = ((t * p.mtiles + mt) * p.ntiles + nt) * p.ksplit;
-                const T *src = ws + tile0 * (long long)(BM * BN) + (m % BM) * BN + (n % BN);
-                T acc = src[0];
+                const A *src = ws + tile0 * (long long)(BM * BN) + (m % BM) * BN + (n % BN);
+                A acc = src[0];
                 for (int s = 1; s < p.ksplit; ++s) acc = addc(acc, src[(long long)s * BM * BN]);
                 const long long orr = group_offset(p.T, t, p.T.sr) + group_offset(p.M, m, p.M.sr) +
                                       group_offset(p.N, n, p.N.sr);
-                T r = mulc(alpha, acc);
-                if (!is_zero_acc(beta)) r = addc(r, mulc(beta, vr[orr]));
-                vr[orr] = r;
+                A r = mulc(alpha, acc);
+                if (!is_zero_acc(beta)) r = addc(r, mulc(beta, widen(vr[orr])));
+                vr[orr] = narrow<T>(r);
             }
         }
 
@@ -585,10 +595,10 @@ namespace sbb {
         /// LDS conflict free (see the derivation in DESIGN.md).
         void tile_layout(bool kfast, int esize, int rows, int bk, int &sr, int &sk) {
             if (kfast) {
-                sr = bk + 4; // 12: = 4 mod 8 (16 B elements) and in {4,12} mod 16 (8 B elements)
+                sr = bk + 4; // 12: = 4 mod 8 (16 B elements), in {4,12} mod 16 (8 B) and in {12,20} mod 32 (4 B)
                 sk = 1;
             } else {
-                sk = rows + (esize == 16 ? 2 : 4);
+                sk = rows + (esize == 16 ? 2 : esize == 8 ? 4 : 8); // = 2 mod 8, 4 mod 16, 8 mod 32 elements
                 sr = 1;
             }
         }
@@ -597,6 +607,7 @@ namespace sbb {
         void launch_mma(ContractParams p, const double *alpha, const void *v0, const void *v1,
                         const double *beta, void *vr, int device, cudaStream_t stream,
                         std::string *describe) {
+            using A = typename Acc<T>::type;
             p.bn = BN;
             {
                 const char *e = std::getenv("SBB_MMA_DEBUG");
@@ -633,15 +644,15 @@ namespace sbb {
             if (ctas >= (1ll << 31)) throw std::runtime_error("contraction: grid too large");
             if (describe) {
                 std::stringstream ss;
-                ss << "mma f64 tile=" << BM << "x" << BN << "x" << BK << " stages=" << STAGES
+                ss << "mma f64" << (sizeof(A) != sizeof(T) ? " (float operands)" : "") << " tile=" << BM << "x" << BN << "x" << BK << " stages=" << STAGES
                    << " T=" << p.T.vol << " M=" << p.M.vol << " N=" << p.N.vol << " K=" << p.K.vol
                    << " ksplit=" << p.ksplit << " ctas=" << ctas << " smem=" << smem
                    << " a_kfast=" << p.a_kfast << " b_kfast=" << p.b_kfast << " loader=" << (BULK ? "tma-bulk" : "cp.async");
                 *describe = ss.str();
                 return;
             }
-            const size_t ws_bytes = (size_t)ctas * BM * BN * sizeof(T);
-            T *ws = (T *)pool_alloc(device, ws_bytes);
+            const size_t ws_bytes = (size_t)ctas * BM * BN * sizeof(A);
+            A *ws = (A *)pool_alloc(device, ws_bytes);
             static size_t attr_smem[64] = {0};
             if (smem > attr_smem[device]) {
                 cuda_check(cudaFuncSetAttribute(contract_mma_kernel<T, BN, BK, STAGES, MINB, BULK>,
@@ -659,8 +670,8 @@ namespace sbb {
             const long long total = p.T.vol * p.M.vol * p.N.vol;
             const unsigned grid =
                 (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(device) * 8);
-            contract_reduce_kernel<T><<<grid, 256, 0, stream>>>(p, ws, (T *)vr, scalar_of<T>(alpha),
-                                                               scalar_of<T>(beta));
+            contract_reduce_kernel<T><<<grid, 256, 0, stream>>>(p, ws, (T *)vr, scalar_of<A>(alpha),
+                                                               scalar_of<A>(beta));
             count_launch();
             cuda_check(cudaGetLastError(), "contract_reduce_kernel launch");
             pool_free(device, ws);
@@ -690,9 +701,9 @@ namespace sbb {
         // An empty contracted range leaves vr = beta*vr: the generic kernel handles K.vol == 0
         const char *force = std::getenv("SBB_CONTRACT_KERNEL");
         const bool f64 = dtype == SBB_F64 || dtype == SBB_C128;
-        bool use_mma = f64 && p.K.vol >= 64 && p.M.vol * p.N.vol >= 256 && p.M.vol >= 8 && p.N.vol >= 8;
+        bool use_mma = p.K.vol >= 64 && p.M.vol * p.N.vol >= 256 && p.M.vol >= 8 && p.N.vol >= 8;
         if (force && std::strcmp(force, "simt") == 0) use_mma = false;
-        if (force && std::strcmp(force, "mma") == 0 && f64 && p.K.vol > 0) use_mma = true;
+        if (force && std::strcmp(force, "mma") == 0 && p.K.vol > 0) use_mma = true;
         if (use_mma) {
             // tile shape: 64x64 (2 CTAs/SM) or 64x32 (3 CTAs/SM, more warps to hide latencies);
             // SBB_MMA_BN overrides for experiments
@@ -709,7 +720,7 @@ namespace sbb {
             }
             const int bk = bk_env ? bk_env : 8;
             // TMA row loader when every tile row is one contiguous, 16-byte aligned run
-            const int esz = dtype == SBB_F64 ? 8 : 16;
+            const int esz = dtype_bytes(dtype);
             auto rows_ok = [&](const Group &R, const long long *rs, const long long *ks, bool isA) {
                 const bool kfast = p.K.n > 0 && (R.n == 0 || ks[0] <= rs[0]);
                 if (kfast) return p.K.n == 1 && ks[0] == 1 && (8 * esz) % 16 == 0;
@@ -720,7 +731,7 @@ namespace sbb {
                 const char *e = std::getenv("SBB_MMA_BULK");
                 bulk_env = e ? std::atoi(e) : 0; // measured slower than per-element cp.async (27.6 vs 30.2 TFLOP/s): 128-byte bulk copies are too small
             }
-            const bool bulk = bulk_env && !std::getenv("SBB_MMA_DEBUG") && bk == 8 && bn == 64 && p.K.vol % 8 == 0 &&
+            const bool bulk = bulk_env && f64 && !std::getenv("SBB_MMA_DEBUG") && bk == 8 && bn == 64 && p.K.vol % 8 == 0 &&
                               rows_ok(p.M, p.M.s0, p.K.s0, true) && rows_ok(p.N, p.N.s1, p.K.s1, false) &&
                               (uintptr_t)v0 % 16 == 0 && (uintptr_t)v1 % 16 == 0 &&
                               [&] { // every other stride must keep 16-byte alignment too
@@ -739,7 +750,9 @@ namespace sbb {
         else launch_mma<T, 64, 8, 4, 2, false>(p, alpha, v0, v1, beta, vr, device, stream, describe);      \
     } while (0)
             if (dtype == SBB_F64) SBB_MMA(double);
-            else SBB_MMA(double2);
+            else if (dtype == SBB_C128) SBB_MMA(double2);
+            else if (dtype == SBB_F32) SBB_MMA(float);
+            else SBB_MMA(float2);
 #undef SBB_MMA
             return;
         }

@@ -191,10 +191,15 @@ namespace sbb {
             const longlong2 *tiles;        // per tile: {source origin | boundary flag in bit 63, destination origin}
         };
 
-        template <class Op, bool SMEM, int EPT, int MINB>
+        /// MASK: the destination element is written only where the masks (MaskType = float, nonzero =
+        /// active; laid out like the destination, either may be null) are nonzero.  This is the
+        /// reference's `select` on the index vectors (tensor.h:1022-1027, blas.h:877-923) done as a
+        /// predicate on the store instead of a stream compaction.
+        template <class Op, bool SMEM, int EPT, int MINB, bool MASK>
         __global__ void __launch_bounds__(NT, MINB)
             permute_kernel(const __grid_constant__ PermParams p, const Tables tab,
-                           const typename Op::T *__restrict__ src, typename Op::Q *dst, Op op) {
+                           const typename Op::T *__restrict__ src, typename Op::Q *dst, Op op,
+                           const float *__restrict__ ma, const float *__restrict__ mb) {
             using T = typename Op::T;
             using Q = typename Op::Q;
             extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -298,6 +303,21 @@ namespace sbb {
                 Tile nxt = cur;
                 if (has_next) nxt = make_tile(e_nxt, tile + G);
                 Q *w = dst + cur.dbase;
+                if (MASK) {
+                    // masked-out destination elements are left untouched
+                    float fa[EPT], fb[EPT];
+#pragma unroll
+                    for (int k = 0; k < EPT; ++k) {
+                        fa[k] = fb[k] = 1.0f;
+                        if (cur.mask_s >> k & 1) {
+                            if (ma) fa[k] = ma[cur.dbase + dof[k]];
+                            if (mb) fb[k] = mb[cur.dbase + dof[k]];
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < EPT; ++k)
+                        if (fa[k] == 0.0f || fb[k] == 0.0f) cur.mask_s &= ~(1u << k);
+                }
                 if (SMEM) {
 #pragma unroll
                     for (int k = 0; k < EPT; ++k)
@@ -346,7 +366,8 @@ namespace sbb {
         /// Zero fill of a strided box (direct variant without source)
         template <class V>
         __global__ void __launch_bounds__(NT)
-            zero_kernel(const __grid_constant__ PermParams p, V *dst) {
+            zero_kernel(const __grid_constant__ PermParams p, V *dst, const float *__restrict__ ma,
+                        const float *__restrict__ mb) {
             const unsigned tid = threadIdx.x;
             int dord[MAXT];
 #pragma unroll
@@ -392,6 +413,8 @@ namespace sbb {
                             ok = ok && (c[q] < lim[q]);
                             if (q < p.nt) d += c[q] * p.tds[q];
                         }
+                        if (ok && ma && ma[dbase + d] == 0.0f) ok = false;
+                        if (ok && mb && mb[dbase + d] == 0.0f) ok = false;
                         if (ok) dst[dbase + d] = zero;
                     }
                 }
@@ -743,9 +766,9 @@ namespace sbb {
             return std::max(n, 1);
         }
 
-        template <class Op, int EPT_ = EPT>
+        template <class Op, bool MASK = false, int EPT_ = EPT>
         void launch_perm(LaunchPlan &lp, const void *src, void *dst, Op op, int device,
-                         cudaStream_t stream) {
+                         cudaStream_t stream, const float *ma = nullptr, const float *mb = nullptr) {
             using T = typename Op::T;
             using Q = typename Op::Q;
             const size_t smem_bytes = (size_t)lp.p.smem_elems * sizeof(T);
@@ -759,22 +782,24 @@ namespace sbb {
                 if (grid_cap() > 0) grid = std::min<unsigned>(grid, (unsigned)grid_cap());
                 {
                     KernelTimer timer("permute", stream);
-                    kernel<<<grid, NT, smem_bytes, stream>>>(lp.p, lp.tab, (const T *)src, (Q *)dst, op);
+                    kernel<<<grid, NT, smem_bytes, stream>>>(lp.p, lp.tab, (const T *)src, (Q *)dst, op,
+                                                             ma, mb);
                 }
                 count_launch();
                 cuda_check(cudaGetLastError(), "permute_kernel launch");
             };
             if (lp.smem)
-                go(permute_kernel<Op, true, EPT_, 2>);
+                go(permute_kernel<Op, true, EPT_, 2, MASK>);
             else
-                go(permute_kernel<Op, false, EPT_, 2>);
+                go(permute_kernel<Op, false, EPT_, 2, MASK>);
         }
 
         template <class V>
-        void launch_zero(LaunchPlan &lp, void *dst, int device, cudaStream_t stream) {
+        void launch_zero(LaunchPlan &lp, void *dst, int device, cudaStream_t stream,
+                         const float *ma = nullptr, const float *mb = nullptr) {
             const unsigned grid =
                 (unsigned)std::min<int64_t>(lp.p.ntiles, (int64_t)dev_info(device).sms * 8);
-            zero_kernel<V><<<grid, NT, 0, stream>>>(lp.p, (V *)dst);
+            zero_kernel<V><<<grid, NT, 0, stream>>>(lp.p, (V *)dst, ma, mb);
             count_launch();
             cuda_check(cudaGetLastError(), "zero_kernel launch");
         }
@@ -826,9 +851,14 @@ namespace sbb {
 
         template <typename T, typename Q>
         void launch_typed(LaunchPlan &lp, const void *src, void *dst, const double *alpha,
-                          bool scale, bool add, int device, cudaStream_t stream) {
-            launch_perm<ElemOp<T, Q>>(lp, src, dst, {make_elem<T>(alpha), scale, add}, device,
-                                           stream);
+                          bool scale, bool add, int device, cudaStream_t stream, const float *ma,
+                          const float *mb) {
+            if (ma || mb)
+                launch_perm<ElemOp<T, Q>, true>(lp, src, dst, {make_elem<T>(alpha), scale, add},
+                                                device, stream, ma, mb);
+            else
+                launch_perm<ElemOp<T, Q>>(lp, src, dst, {make_elem<T>(alpha), scale, add}, device,
+                                          stream);
         }
 
         struct Decision {
@@ -867,7 +897,8 @@ namespace sbb {
         /// Run one box of at most KD (canonical) dims
         void run_box(const Canon &c0, const void *src, int dt0, void *dst, int dt1,
                      const double *alpha, bool add, int device, cudaStream_t stream,
-                     std::string *describe) {
+                     std::string *describe, const float *ma, const float *mb) {
+            const bool masked = ma || mb; // masks are per element: no widening, typed kernel
             const bool is_zero = alpha[0] == 0 && (alpha[1] == 0 || dt0 == SBB_F32 ||
                                                    dt0 == SBB_F64 || dt0 == SBB_I32);
             const bool is_one = alpha[0] == 1 && (alpha[1] == 0 || dt0 == SBB_F32 ||
@@ -882,9 +913,9 @@ namespace sbb {
             std::string key;
             {
                 auto put = [&](const void *ptr, size_t n) { key.append((const char *)ptr, n); };
-                const int flags[7] = {dt0, dt1, is_zero, is_one, add,
+                const int flags[8] = {dt0, dt1, is_zero, is_one, add,
                                       (int)(((uintptr_t)src & 15) | (((uintptr_t)dst & 15) << 4)),
-                                      device};
+                                      device, masked};
                 put(flags, sizeof flags);
                 put(&c0.nd, sizeof c0.nd);
                 put(c0.size.data(), c0.size.size() * sizeof(int));
@@ -905,22 +936,23 @@ namespace sbb {
                 if (hit != cache.end()) {
                     c = hit->second.c, lp = hit->second.lp, es = hit->second.es;
                 } else {
-                    es = promote(c, dtype_size(dt1), nullptr, dst, false);
+                    es = masked ? dtype_size(dt1) : promote(c, dtype_size(dt1), nullptr, dst, false);
                     lp = plan_launch(c, es, NT * EPT, false);
                     if (!describe) remember(c, lp, es);
                 }
                 if (describe) {
-                    ds << "zero es=" << es << " tile=" << lp.p.tile_elems << " ntiles=" << lp.p.ntiles;
+                    ds << (masked ? "masked " : "") << "zero es=" << es << " tile=" << lp.p.tile_elems << " ntiles=" << lp.p.ntiles;
                     *describe = ds.str();
                     return;
                 }
                 char *d = (char *)dst + c.doff * es;
-                if (es == 16) launch_zero<uint4>(lp, d, device, stream);
-                else if (es == 8) launch_zero<uint2>(lp, d, device, stream);
-                else launch_zero<unsigned>(lp, d, device, stream);
+                const float *xa = ma ? ma + c.doff : nullptr, *xb = mb ? mb + c.doff : nullptr;
+                if (es == 16) launch_zero<uint4>(lp, d, device, stream, xa, xb);
+                else if (es == 8) launch_zero<uint2>(lp, d, device, stream, xa, xb);
+                else launch_zero<unsigned>(lp, d, device, stream, xa, xb);
                 return;
             }
-            if (dt0 == dt1 && is_one && !add) {
+            if (dt0 == dt1 && is_one && !add && !masked) {
                 int es;
                 LaunchPlan lp;
                 if (hit != cache.end()) {
@@ -961,7 +993,7 @@ namespace sbb {
                 }
             }
             if (describe) {
-                ds << (lp.smem ? "typed tiled" : "typed direct") << " es=" << es0 << "->" << es1
+                ds << (masked ? "masked " : "") << (lp.smem ? "typed tiled" : "typed direct") << " es=" << es0 << "->" << es1
                    << " tile=" << lp.p.tile_elems << " ntiles=" << lp.p.ntiles
                    << " scale=" << !is_one << " add=" << add;
                 *describe = ds.str();
@@ -972,7 +1004,8 @@ namespace sbb {
             const bool scale = !is_one;
 #define SBB_TYPED(DT0, DT1, T, Q)                                                                  \
     if (dt0 == DT0 && dt1 == DT1) {                                                                \
-        launch_typed<T, Q>(lp, s, d, alpha, scale, add, device, stream);                           \
+        launch_typed<T, Q>(lp, s, d, alpha, scale, add, device, stream,                            \
+                           ma ? ma + c.doff : nullptr, mb ? mb + c.doff : nullptr);                \
         return;                                                                                    \
     }
             SBB_TYPED(SBB_F32, SBB_F32, float, float)
@@ -1004,7 +1037,7 @@ namespace sbb {
 
     void permute_copy(const sbk_box_desc &box, const void *src, int dt0, void *dst, int dt1,
                       const double *alpha, bool add, int device, cudaStream_t stream,
-                      std::string *describe) {
+                      std::string *describe, const float *ma, const float *mb) {
         if (box.nd < 0 || box.nd > SBK_MAX_DIMS) throw std::runtime_error("permute copy: bad nd");
         if (!convertible(dt0, dt1))
             throw std::runtime_error("permute copy: unsupported type combination");
@@ -1016,7 +1049,7 @@ namespace sbb {
             return;
         }
         if (c.nd <= KD) {
-            run_box(c, src, dt0, dst, dt1, alpha, add, device, stream, describe);
+            run_box(c, src, dt0, dst, dt1, alpha, add, device, stream, describe, ma, mb);
             return;
         }
         // More than KD irreducible dims: iterate over the slowest ones on the host
@@ -1030,7 +1063,7 @@ namespace sbb {
                 sub.soff += idx[k] * c.ss[KD + k];
                 sub.doff += idx[k] * c.ds[KD + k];
             }
-            run_box(sub, src, dt0, dst, dt1, alpha, add, device, stream, describe);
+            run_box(sub, src, dt0, dst, dt1, alpha, add, device, stream, describe, ma, mb);
             if (describe) return;
             int k = 0;
             for (; k < outer; ++k) {

@@ -442,7 +442,8 @@ namespace sbb {
 
     void execute_copy(const CopyPlan &plan, const CopyArgs &args, int dtype0, int dtype1,
                       const double *alpha, const std::vector<Buffer> &v0,
-                      const std::vector<Buffer> &v1, Comm *comm) {
+                      const std::vector<Buffer> &v1, Comm *comm,
+                      const std::vector<Buffer> *mask_a, const std::vector<Buffer> *mask_b) {
         // a rank without work still takes part in the barrier of the peer-memory transport
         if (plan.ops.empty() && !(comm && comm->nccl && comm->p2p && plan.any_comm)) return;
         const int es0 = dtype_bytes(dtype0), es1 = dtype_bytes(dtype1);
@@ -507,7 +508,7 @@ namespace sbb {
                 d[c].staged = pool_alloc(home, d[c].bytes);
                 d[c].ptr = (char *)d[c].staged;
                 // keep what the copy does not overwrite (Copy ops never overlap, see plan.cpp)
-                if (args.add || written[c] < vol) {
+                if (args.add || written[c] < vol || mask_a || mask_b) {
                     use_device(home);
                     cuda_check(cudaMemcpyAsync(d[c].ptr, v1[c].ptr, d[c].bytes,
                                                cudaMemcpyHostToDevice, hs.stream),
@@ -519,6 +520,38 @@ namespace sbb {
             }
             devs.insert(d[c].device);
         }
+
+        // Masks of the destination components (MaskType = float, laid out like the component): host
+        // masks are staged next to the component's data
+        std::vector<const float *> mA(v1.size(), nullptr), mB(v1.size(), nullptr);
+        std::vector<std::pair<int, void *>> mask_staged;
+        for (int which = 0; which < 2; ++which) {
+            const std::vector<Buffer> *m = which ? mask_b : mask_a;
+            if (!m) continue;
+            if (m->size() != v1.size()) throw std::runtime_error("copy: one mask per component expected");
+            for (size_t c = 0; c < v1.size(); ++c) {
+                if (!d[c].used) continue;
+                const Buffer &b = (*m)[c];
+                if (!b.ptr) throw std::runtime_error("copy: null mask for a non-empty component");
+                const float *ptr = (const float *)b.ptr;
+                if (b.host) {
+                    const size_t bytes = d[c].bytes / es1 * sizeof(float);
+                    void *st = pool_alloc(d[c].device, bytes);
+                    use_device(d[c].device);
+                    cuda_check(cudaMemcpyAsync(st, b.ptr, bytes, cudaMemcpyHostToDevice,
+                                               device_state(d[c].device).stream),
+                               "cudaMemcpyAsync H2D (mask)");
+                    mask_staged.emplace_back(d[c].device, st);
+                    ptr = (const float *)st;
+                } else {
+                    enable_peer(d[c].device, b.device);
+                    devs.insert(b.device);
+                }
+                (which ? mB : mA)[c] = ptr;
+            }
+        }
+        auto ma = [&](int comp) { return mA[comp]; };
+        auto mb = [&](int comp) { return mB[comp]; };
 
         // Several devices in one process: order their streams before and after (the reference's
         // causalConnectTo, platform.h:371-409)
@@ -583,7 +616,7 @@ namespace sbb {
                 use_device(b.device);
                 desc.soff = op.soff, desc.doff = op.doff;
                 permute_copy(desc, a.ptr, dtype0, b.ptr, dtype1, alpha, args.add, b.device,
-                             stream_for(b.device));
+                             stream_for(b.device), nullptr, ma(op.dst_comp), mb(op.dst_comp));
                 break;
             }
             case BoxOp::Pack: {
@@ -604,15 +637,16 @@ namespace sbb {
                 desc.soff = op.soff, desc.doff = op.doff;
                 const char *from = use_p2p ? p2p_recv_base[op.peer] : recvbuf + seg_recv[op.peer];
                 permute_copy(desc, from, wire_dtype, b.ptr, dtype1, one, args.add, b.device,
-                             stream_for(b.device));
+                             stream_for(b.device), nullptr, ma(op.dst_comp), mb(op.dst_comp));
                 break;
             }
             case BoxOp::Zero: {
                 const Resolved &b = d[op.dst_comp];
                 use_device(b.device);
                 desc.doff = op.doff;
+                // uncovered destination: only the destination's own mask applies (dist.h:2363-2367)
                 permute_copy(desc, nullptr, dtype1, b.ptr, dtype1, zero, false, b.device,
-                             stream_for(b.device));
+                             stream_for(b.device), nullptr, nullptr, mb(op.dst_comp));
                 break;
             }
             }
@@ -802,6 +836,7 @@ namespace sbb {
             use_device(home);
             cuda_check(cudaStreamSynchronize(hs.stream), "cudaStreamSynchronize");
         }
+        for (auto &m : mask_staged) pool_free(m.first, m.second);
         for (auto &r : s) pool_free(home, r.staged);
         for (auto &r : d) pool_free(home, r.staged);
         pool_free(home, sendbuf);

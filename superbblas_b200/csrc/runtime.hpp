@@ -58,7 +58,9 @@ namespace sbb {
 
     void execute_copy(const CopyPlan &plan, const CopyArgs &args, int dtype0, int dtype1,
                       const double *alpha, const std::vector<Buffer> &v0,
-                      const std::vector<Buffer> &v1, Comm *comm);
+                      const std::vector<Buffer> &v1, Comm *comm,
+                      const std::vector<Buffer> *mask_a = nullptr,
+                      const std::vector<Buffer> *mask_b = nullptr);
 
     long long launch_count(bool reset);
 

@@ -157,10 +157,50 @@ def make_copy_data(case, seed, consistent=False):
     return v0, v1
 
 
-def oracle_copy(case, v0, v1):
+def make_masks(case, seed, density=0.5):
+    """Compatible masks (MaskType = float32) for a copy case: one global mask on the source lattice;
+    mask0[i] is its restriction to source part i, mask1[j] holds, for every destination element
+    inside the copied range, the mask value of the source element that lands there, and arbitrary
+    values elsewhere.  This is the only kind of mask pair the reference accepts (equal counts per
+    box, tensor.h:1022-1027).  Nonzero values other than 1 are used on purpose."""
+    rng = np.random.default_rng(seed * 31 + 7)
+    dim0, dim1 = np.asarray(case["dim0"], dtype=np.int64), np.asarray(case["dim1"], dtype=np.int64)
+    o0, o1 = case["o0"], case["o1"]
+    n0 = len(o0)
+    vol0 = int(np.prod(dim0))
+    g = (rng.random(vol0) < density) * rng.choice([1.0, 2.0, -1.0, 0.5], size=vol0)
+    g = g.astype(np.float32)
+    gs = np.asarray(O.get_strides(case["dim0"], case["co"]), dtype=np.int64)
+    mask0 = []
+    for i in range(case["p0"].shape[0]):
+        c = (O._local_coords(case["p0"][i, 1], case["co"]) + case["p0"][i, 0]) % dim0
+        mask0.append(np.ascontiguousarray(g[(c * gs).sum(axis=1)]) if c.shape[0] else
+                     np.zeros(0, dtype=np.float32))
+    size1 = [int(case["size0"][o0.index(l)]) if l in o0 else 1 for l in o1]
+    mask1 = []
+    for j in range(case["p1"].shape[0]):
+        sj = case["p1"][j, 1]
+        n = int(np.prod(sj))
+        m = (rng.random(n) < density).astype(np.float32)
+        if n:
+            c1 = (O._local_coords(sj, case["co"]) + case["p1"][j, 0]) % dim1
+            inr = O._in_interval(case["from1"], size1, case["dim1"], c1)
+            u1 = (c1 - np.asarray(case["from1"], dtype=np.int64)) % dim1
+            c0 = np.zeros((n, n0), dtype=np.int64)
+            for k, l in enumerate(o0):
+                if l in o1:
+                    c0[:, k] = u1[:, o1.index(l)]
+            c0 = (c0 + np.asarray(case["from0"], dtype=np.int64)) % dim0
+            m[inr] = g[(c0[inr] * gs).sum(axis=1)]
+        mask1.append(m)
+    return mask0, mask1
+
+
+def oracle_copy(case, v0, v1, mask0=None, mask1=None):
     out = [x.copy() for x in v1]
     O.copy(case["alpha"], case["p0"], case["o0"], case["from0"], case["size0"], case["dim0"], v0,
-           case["p1"], case["o1"], case["from1"], case["dim1"], out, case["co"], case["copyadd"])
+           case["p1"], case["o1"], case["from1"], case["dim1"], out, case["co"], case["copyadd"],
+           mask0=mask0, mask1=mask1)
     return out
 
 

@@ -166,6 +166,44 @@ int main() {
         for (int i = 0; i < P; ++i) cudaFree(v0[i]), cudaFree(v1[i]);
     }
 
+    // --- masked copy (MaskType masks on both tensors): even sites of a permuted field -----------------------
+    {
+        Coor<4> dim0{L, L, L, Lt}, dim1{Lt, L, L, L};
+        PartitionItem<4> p0{Coor<4>{}, dim0}, p1{Coor<4>{}, dim1};
+        std::size_t vol = detail::volume(dim0);
+        std::vector<Z> h0(vol), h1(vol, Z{-5, 5});
+        std::vector<MaskType> m0(vol), m1(vol);
+        for (int x = 0; x < L; ++x)
+            for (int y = 0; y < L; ++y)
+                for (int z = 0; z < L; ++z)
+                    for (int t = 0; t < Lt; ++t) {
+                        std::size_t i0 = x + L * (y + L * (z + L * t));
+                        std::size_t i1 = t + Lt * (z + L * (y + L * x));
+                        h0[i0] = Z((double)i0, 0.5);
+                        m0[i0] = m1[i1] = (x + y + z + t) % 2 == 0 ? 1.0f : 0.0f;
+                    }
+        Z *d0 = to_device(h0), *d1 = to_device(h1);
+        MaskType *dm0 = to_device(m0), *dm1 = to_device(m1);
+        const Z *src = d0;
+        const MaskType *pm0 = dm0, *pm1 = dm1;
+        copy<4, 4>(Z{2}, &p0, 1, "xyzt", {}, dim0, dim0, &src, &pm0, &gpu, &p1, 1, "tzyx", {}, dim1, &d1,
+                   &pm1, &gpu, FastToSlow, Copy);
+        sync(gpu);
+        std::vector<Z> r = to_host(d1, vol);
+        std::size_t bad = 0;
+        for (int x = 0; x < L; ++x)
+            for (int y = 0; y < L; ++y)
+                for (int z = 0; z < L; ++z)
+                    for (int t = 0; t < Lt; ++t) {
+                        std::size_t i0 = x + L * (y + L * (z + L * t));
+                        std::size_t i1 = t + Lt * (z + L * (y + L * x));
+                        Z want = (x + y + z + t) % 2 == 0 ? Z{2} * h0[i0] : Z{-5, 5};
+                        if (r[i1] != want) ++bad;
+                    }
+        CHECK(bad == 0);
+        cudaFree(d0), cudaFree(d1), cudaFree(dm0), cudaFree(dm1);
+    }
+
     // --- error behaviour ------------------------------------------------------------------------------------
     {
         Coor<2> d{2, 2};

@@ -3,7 +3,7 @@
 // drop-in header include/superbblas.h.  The reference's `main` runs ~1.2 million contractions, twice;
 // this wrapper keeps the test templates untouched and selects which part of the enumeration to run:
 //
-//   ref_contract_wrapper [--nt=0|1] [--type=d|z] [--components=N] [--cpu]
+//   ref_contract_wrapper [--nt=0|1] [--type=s|d|c|z] [--components=N] [--cpu]
 //
 // --nt picks the number of batch labels (the outermost enumeration level, test_for_A<NT,T>),
 // --cpu passes host (CPU-context) components instead of GPU ones (they are staged through the GPU).
@@ -27,6 +27,8 @@ int main(int argc, char **argv) {
         std::vector<superbblas::detail::Cpu> xpus;
         for (const auto &i : ctx) xpus.push_back(i.toCpu(0));
         if (type == 'd') nt ? test_for_A<1, double>(ctx, xpus) : test_for_A<0, double>(ctx, xpus);
+        else if (type == 's') nt ? test_for_A<1, float>(ctx, xpus) : test_for_A<0, float>(ctx, xpus);
+        else if (type == 'c') nt ? test_for_A<1, std::complex<float>>(ctx, xpus) : test_for_A<0, std::complex<float>>(ctx, xpus);
         else nt ? test_for_A<1, std::complex<double>>(ctx, xpus) : test_for_A<0, std::complex<double>>(ctx, xpus);
     } else {
         std::vector<Context> ctx;
@@ -34,6 +36,8 @@ int main(int argc, char **argv) {
         std::vector<superbblas::detail::Gpu> xpus;
         for (const auto &i : ctx) xpus.push_back(i.toGpu(0));
         if (type == 'd') nt ? test_for_A<1, double>(ctx, xpus) : test_for_A<0, double>(ctx, xpus);
+        else if (type == 's') nt ? test_for_A<1, float>(ctx, xpus) : test_for_A<0, float>(ctx, xpus);
+        else if (type == 'c') nt ? test_for_A<1, std::complex<float>>(ctx, xpus) : test_for_A<0, std::complex<float>>(ctx, xpus);
         else nt ? test_for_A<1, std::complex<double>>(ctx, xpus) : test_for_A<0, std::complex<double>>(ctx, xpus);
     }
     clearCaches();

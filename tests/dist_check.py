@@ -69,8 +69,13 @@ def main():
     for it in range(args.cases):
         nc0, nc1 = int(rng.integers(1, 3)), int(rng.integers(1, 3))
         case = C.random_copy_case(rng, nparts0=world * nc0, nparts1=world * nc1)
-        v0, v1 = C.make_copy_data(case, 100 + it, consistent=case["copyadd"] == 0)
-        want = C.oracle_copy(case, v0, v1)
+        masked = it % 3 == 2  # every third case carries (compatible) masks on both tensors
+        v0, v1 = C.make_copy_data(case, 100 + it, consistent=masked or case["copyadd"] == 0)
+        m0 = m1 = mm0 = mm1 = None
+        if masked:
+            m0, m1 = C.make_masks(case, 100 + it)
+            mm0, mm1 = m0[rank * nc0:(rank + 1) * nc0], m1[rank * nc1:(rank + 1) * nc1]
+        want = C.oracle_copy(case, v0, v1, m0, m1)
         mine0 = [x.copy() for x in v0[rank * nc0:(rank + 1) * nc0]]
         mine1 = [x.copy() for x in v1[rank * nc1:(rank + 1) * nc1]]
         if args.backend == "gloo":
@@ -80,15 +85,30 @@ def main():
                                      case["size0"], case["dim0"], case["p1"], nc1, case["o1"],
                                      case["from1"], case["dim1"], world, rank, case["co"],
                                      case["copyadd"], zero)
+            tmp = None
+            if masked and not zero:
+                # step 1 of a masked copy (capi.cpp, sbb_copy): mask0 travels to the destination
+                # layout as an ordinary float copy with the same geometry
+                F = np.dtype(np.float32)
+                mops, mwire = sb.copy_plan(4, case["p0"], nc0, case["o0"], case["from0"],
+                                           case["size0"], case["dim0"], case["p1"], nc1, case["o1"],
+                                           case["from1"], case["dim1"], world, rank, case["co"], 0,
+                                           False)
+                tmp = [np.full(x.size, np.nan, dtype=np.float32) for x in mine1]
+                run_rank(mops, mwire, rank, world, nc0, nc1, mm0, tmp, 1, 0, F, F,
+                         gloo_exchange(mwire, rank, F))
             run_rank(ops, wire, rank, world, nc0, nc1, mine0, mine1, case["alpha"], case["copyadd"],
-                     case["T"], case["Q"], gloo_exchange(wire, rank, Wt))
+                     case["T"], case["Q"], gloo_exchange(wire, rank, Wt), mask_a=tmp,
+                     mask_b=mm1 if masked else None)
             got = mine1
         else:
             d0 = [torch.from_numpy(x).cuda() for x in mine0]
             d1 = [torch.from_numpy(x).cuda() for x in mine1]
+            dm0 = [torch.from_numpy(x).cuda() for x in mm0] if masked else None
+            dm1 = [torch.from_numpy(x).cuda() for x in mm1] if masked else None
             sb.copy(case["alpha"], case["p0"], nc0, case["o0"], case["from0"], case["size0"],
-                    case["dim0"], d0, None, gpu, case["p1"], nc1, case["o1"], case["from1"],
-                    case["dim1"], d1, None, gpu, case["co"], case["copyadd"], comm=comm)
+                    case["dim0"], d0, dm0, gpu, case["p1"], nc1, case["o1"], case["from1"],
+                    case["dim1"], d1, dm1, gpu, case["co"], case["copyadd"], comm=comm)
             sb.sync(gpu)
             got = [x.cpu().numpy() for x in d1]
         for j, g in enumerate(got):

@@ -13,17 +13,24 @@ def to_host(tensors):
     return [t.cpu().numpy() for t in tensors]
 
 
-def run_copy(case, v0, v1, host0=(), host1=()):
+def run_copy(case, v0, v1, host0=(), host1=(), mask0=None, mask1=None):
     """sb.copy with every part a component of one process on cuda:0 (parts listed in host0/host1
-    stay in host memory, i.e. CPU contexts)."""
+    stay in host memory, i.e. CPU contexts; their masks too)."""
     P0, P1 = case["p0"].shape[0], case["p1"].shape[0]
     gpu, cpu = sb.createGpuContext(0), sb.createCpuContext()
     d0 = [np.ascontiguousarray(a.copy()) if i in host0 else to_dev([a])[0] for i, a in enumerate(v0)]
     d1 = [np.ascontiguousarray(a.copy()) if j in host1 else to_dev([a])[0] for j, a in enumerate(v1)]
     ctx0 = [cpu if i in host0 else gpu for i in range(P0)]
     ctx1 = [cpu if j in host1 else gpu for j in range(P1)]
+    m0 = m1 = None
+    if mask0 is not None:
+        m0 = [np.ascontiguousarray(a.copy()) if i in host0 else to_dev([a])[0]
+              for i, a in enumerate(mask0)]
+    if mask1 is not None:
+        m1 = [np.ascontiguousarray(a.copy()) if j in host1 else to_dev([a])[0]
+              for j, a in enumerate(mask1)]
     sb.copy(case["alpha"], case["p0"], P0, case["o0"], case["from0"], case["size0"], case["dim0"],
-            d0, None, ctx0, case["p1"], P1, case["o1"], case["from1"], case["dim1"], d1, None, ctx1,
+            d0, m0, ctx0, case["p1"], P1, case["o1"], case["from1"], case["dim1"], d1, m1, ctx1,
             case["co"], case["copyadd"])
     sb.sync(gpu)
     return [x if isinstance(x, np.ndarray) else x.cpu().numpy() for x in d1]

@@ -18,8 +18,11 @@ def _indices(size, stride, off, rot=0):
 
 
 def run_rank(ops, wire, rank, nranks, ncomp0, ncomp1, v0_local, v1_local, alpha, copyadd, T, Q,
-             exchange):
-    """Run the ops of one rank. `exchange(send: {peer: array}) -> {peer: array}` moves messages."""
+             exchange, mask_a=None, mask_b=None):
+    """Run the ops of one rank. `exchange(send: {peer: array}) -> {peer: array}` moves messages.
+    mask_a / mask_b: optional float32 masks per local destination component (laid out like it): an
+    element is written only where both are nonzero; zero-fills look at mask_b only (capi.cpp,
+    sbb_copy; runtime.cpp, execute_copy)."""
     T, Q = np.dtype(T), np.dtype(Q)
     one = (np.real(alpha) == 1 and np.imag(alpha) == 0)
     # wire element type: Q, except T when adding with a type change (runtime.cpp, execute_copy)
@@ -31,7 +34,17 @@ def run_rank(ops, wire, rank, nranks, ncomp0, ncomp1, v0_local, v1_local, alpha,
             x = O._scale(alpha, x, T)
         return x
 
-    def store(dst, idx, x, XT):
+    def keep(comp, idx, zero=False):
+        k = np.ones(idx.size, dtype=bool)
+        if mask_a is not None and not zero:
+            k &= mask_a[comp][idx] != 0
+        if mask_b is not None:
+            k &= mask_b[comp][idx] != 0
+        return k
+
+    def store(dst, idx, x, XT, comp):
+        k = keep(comp, idx)
+        idx, x = idx[k], x[k]
         if copyadd == 0:
             dst[idx] = x.astype(dst.dtype)
         else:
@@ -54,11 +67,14 @@ def run_rank(ops, wire, rank, nranks, ncomp0, ncomp1, v0_local, v1_local, alpha,
             src = v0_local[op["src"] - rank * ncomp0]
             dst = v1_local[op["dst"] - rank * ncomp1]
             x = transformed(src[_indices(op["size"], op["sstride"], op["soff"])])
-            store(dst, _indices(op["size"], op["dstride"], op["doff"], op.get("rot", 0)), x, T)
+            store(dst, _indices(op["size"], op["dstride"], op["doff"], op.get("rot", 0)), x, T,
+                  op["dst"] - rank * ncomp1)
         elif op["kind"] == "unpack":
             dst = v1_local[op["dst"] - rank * ncomp1]
             x = recv[op["peer"]][_indices(op["size"], op["sstride"], op["soff"])]
-            store(dst, _indices(op["size"], op["dstride"], op["doff"]), x, Wt)
+            store(dst, _indices(op["size"], op["dstride"], op["doff"]), x, Wt,
+                  op["dst"] - rank * ncomp1)
         elif op["kind"] == "zero":
             dst = v1_local[op["dst"] - rank * ncomp1]
-            dst[_indices(op["size"], op["dstride"], op["doff"])] = 0
+            idx = _indices(op["size"], op["dstride"], op["doff"])
+            dst[idx[keep(op["dst"] - rank * ncomp1, idx, zero=True)]] = 0

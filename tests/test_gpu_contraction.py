@@ -78,7 +78,7 @@ def test_config1_contractions(gu, co):
         assert ok, (o_r, err)
 
 
-@pytest.mark.parametrize("dtype", [np.complex128, np.float64, np.complex64])
+@pytest.mark.parametrize("dtype", [np.complex128, np.float64, np.complex64, np.float32])
 def test_distillation_shape_reduced(gu, dtype):
     """BASELINE config 2 at reduced size: V[c,x,y,z,t,n]^H V[c,x,y,z,t,m] -> [t,n,m]; also the
     z,t-partitioned variant of config 4 with 8 components (partials reduced with Add)."""

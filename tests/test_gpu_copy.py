@@ -30,6 +30,78 @@ def test_random_copies_bit_exact(gu, seed):
             assert C.bits_equal(g, w), (seed, it, j, case)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_masked_copies_bit_exact(gu, seed):
+    """Masks (tensor.h:1022-1027, dist.h:944-970): compatible mask pairs as the
+    reference requires them, on random geometries, partitions, types, alpha, Copy/Add; some
+    components (and their masks) in host memory."""
+    rng = np.random.default_rng(1500 + seed)
+    for it in range(40):
+        case = C.random_copy_case(rng, max_dim=7)
+        v0, v1 = C.make_copy_data(case, seed * 100 + it, consistent=True)
+        m0, m1 = C.make_masks(case, seed * 100 + it, density=[0.5, 0.1, 0.9][it % 3])
+        want = C.oracle_copy(case, v0, v1, m0, m1)
+        h0 = [i for i in range(len(v0)) if seed % 2 and rng.random() < 0.3]
+        h1 = [j for j in range(len(v1)) if seed % 2 and rng.random() < 0.3]
+        got = gu.run_copy(case, v0, v1, host0=h0, host1=h1, mask0=m0, mask1=m1)
+        for j, (g, w) in enumerate(zip(got, want)):
+            assert C.bits_equal(g, w), (seed, it, j, case)
+
+
+def test_one_sided_masks(gu):
+    """Only one of the two masks given: an element moves iff the given mask is nonzero at its
+    source (mask0) or at its destination (mask1); everything else is untouched."""
+    rng = np.random.default_rng(1600)
+    for it in range(60):
+        case = C.random_copy_case(rng, max_dim=6)
+        v0, v1 = C.make_copy_data(case, 700 + it, consistent=True)
+        m0, m1 = C.make_masks(case, 700 + it)
+        if it % 2:
+            m0 = None
+        else:
+            m1 = None
+        want = C.oracle_copy(case, v0, v1, m0, m1)
+        got = gu.run_copy(case, v0, v1, mask0=m0, mask1=m1)
+        for j, (g, w) in enumerate(zip(got, want)):
+            assert C.bits_equal(g, w), (it, j, case)
+
+
+def test_masked_even_odd_lattice(gu):
+    """Chroma-style even/odd checkerboard on a 16^3 x 32 x 4 x 3 field, permuted "xyztsc" ->
+    "cstzyx": the even copy followed by the odd copy equals the unmasked copy and each half leaves
+    the other half untouched."""
+    import torch
+    dim0, dim1 = [16, 16, 16, 32, 4, 3], [3, 4, 32, 16, 16, 16]
+    p0, p1 = np.array([[[0] * 6, dim0]], dtype=np.int32), np.array([[[0] * 6, dim1]], dtype=np.int32)
+    vol = int(np.prod(dim0))
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = torch.view_as_complex(torch.randn(vol, 2, generator=g, device="cuda", dtype=torch.float64))
+    # parity of x+y+z+t; FastToSlow: x fastest => torch shape is the reversed dim list
+    ax = [torch.arange(d, device="cuda") for d in dim0]
+    par0 = (ax[0].view(1, 1, 1, 1, 1, -1) + ax[1].view(1, 1, 1, 1, -1, 1) + ax[2].view(1, 1, 1, -1, 1, 1) +
+            ax[3].view(1, 1, -1, 1, 1, 1) + 0 * ax[4].view(1, -1, 1, 1, 1, 1) +
+            0 * ax[5].view(-1, 1, 1, 1, 1, 1)) % 2
+    even0 = (par0 == 0).to(torch.float32).contiguous().view(-1)
+    odd0 = 1 - even0
+    perm = lambda m: m.view(*reversed(dim0)).permute(5, 4, 3, 2, 1, 0).contiguous().view(-1)
+    even1, odd1 = perm(even0), perm(odd0)
+    gpu = sb.createGpuContext(0)
+
+    def run(m0, m1, dst):
+        sb.copy(1, p0, 1, "xyztsc", [0] * 6, dim0, dim0, [a], m0, gpu, p1, 1, "cstzyx", [0] * 6, dim1,
+                [dst], m1, gpu, sb.FastToSlow, sb.Copy)
+        sb.sync(gpu)
+    full = torch.zeros_like(a)
+    run(None, None, full)
+    sentinel = torch.full_like(a, 7 - 3j)
+    b = sentinel.clone()
+    run([even0], [even1], b)
+    assert torch.equal(torch.view_as_real(b)[odd1 != 0], torch.view_as_real(sentinel)[odd1 != 0])
+    assert torch.equal(torch.view_as_real(b)[even1 != 0], torch.view_as_real(full)[even1 != 0])
+    run([odd0], [odd1], b)
+    assert torch.equal(torch.view_as_real(b), torch.view_as_real(full))
+
+
 def test_host_components_are_staged_through_the_gpu(gu):
     rng = np.random.default_rng(600)
     for it in range(40):
@@ -189,8 +261,8 @@ def test_errors(gu):
     with pytest.raises(RuntimeError):
         sb.copy(1, p, 1, "xyz", [0, 0], [2, 2], [2, 2], [x], None, gpu, p, 1, "xy", [0, 0], [2, 2],
                 [y], None, gpu, sb.FastToSlow, sb.Copy)
-    with pytest.raises(RuntimeError, match="masks"):
-        sb.copy(1, p, 1, "xy", [0, 0], [2, 2], [2, 2], [x], [None], gpu, p, 1, "xy", [0, 0], [2, 2],
+    with pytest.raises(RuntimeError, match="masks must be float32"):
+        sb.copy(1, p, 1, "xy", [0, 0], [2, 2], [2, 2], [x], [x], gpu, p, 1, "xy", [0, 0], [2, 2],
                 [y], None, gpu, sb.FastToSlow, sb.Copy)
     # empty and degenerate inputs
     p0 = np.array([[[0, 0], [0, 0]]], dtype=np.int32)

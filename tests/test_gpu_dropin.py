@@ -28,8 +28,7 @@ def _run_reference_suite(args, timeout=900):
     assert "Everything went ok!" in r.stdout
 
 
-@pytest.mark.parametrize("nt", [0, 1])
-@pytest.mark.parametrize("typ", ["d", "z"])
+@pytest.mark.parametrize("nt,typ", [(0, "d"), (1, "d"), (0, "z"), (1, "z"), (1, "s"), (0, "c")])
 def test_reference_own_contraction_suite(nt, typ):
     """The reference's tests/contract.cpp, unmodified (included from /root/reference at build time
     by tests/cxx/ref_contract_wrapper.cpp), compiled against include/superbblas.h and run on the GPU:

@@ -73,6 +73,29 @@ def test_copy_random_bit_exact(reflib, seed):
 
 
 @pytest.mark.parametrize("seed", range(4))
+def test_masked_copy_random_bit_exact(reflib, seed):
+    """Masked copies (MaskType masks on both tensors, tensor.h:1022-1027): the reference with
+    compatible masks against the oracle, bit for bit."""
+    rng = np.random.default_rng(300 + seed)
+    checked = 0
+    for it in range(80):
+        case = C.random_copy_case(rng)
+        if not C.safe_for_reference(case):
+            continue
+        checked += 1
+        v0, v1 = C.make_copy_data(case, seed * 100 + it, consistent=True)
+        m0, m1 = C.make_masks(case, seed * 100 + it, density=[0.5, 0.1, 0.9][it % 3])
+        want = [x.copy() for x in v1]
+        reflib.copy(case["alpha"], case["p0"], case["o0"], case["from0"], case["size0"],
+                    case["dim0"], v0, case["p1"], case["o1"], case["from1"], case["dim1"], want,
+                    case["co"], case["copyadd"], mask0=m0, mask1=m1)
+        got = C.oracle_copy(case, v0, v1, m0, m1)
+        for j, (g, w) in enumerate(zip(got, want)):
+            assert C.bits_equal(g, w), (seed, it, j, case)
+    assert checked >= 30
+
+
+@pytest.mark.parametrize("seed", range(4))
 def test_contraction_random(reflib, seed):
     rng = np.random.default_rng(200 + seed)
     for it in range(40):
