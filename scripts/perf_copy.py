@@ -14,19 +14,30 @@ stream = torch.cuda.ExternalStream(sb.get_stream(0))
 out = {}
 
 
-def run(name, o0, dim0, o1, dtype, from1=None, reps=20):
+def run(name, o0, dim0, o1, dtype, from1=None, reps=20, masked=False):
     n = len(dim0)
     dim1 = [dim0[o0.index(l)] for l in o1]
     vol = int(np.prod(dim0))
-    real = torch.float64 if dtype == torch.complex128 else torch.float32
-    x = torch.view_as_complex(torch.rand(vol, 2, device="cuda", dtype=real))
+    if dtype.is_complex:
+        real = torch.float64 if dtype == torch.complex128 else torch.float32
+        x = torch.view_as_complex(torch.rand(vol, 2, device="cuda", dtype=real))
+    else:
+        x = torch.rand(vol, device="cuda", dtype=dtype)
     y = torch.zeros_like(x)
+    m0 = m1 = None
+    if masked:  # random 50 % mask on the source, carried to the destination layout
+        m0 = (torch.rand(vol, device="cuda") < 0.5).to(torch.float32)
+        m1 = torch.zeros_like(m0)
+        sb.copy(1, p0 := np.array([[[0] * n, dim0]], dtype=np.int32), 1, o0, [0] * n, dim0, dim0, [m0],
+                None, gpu, np.array([[[0] * n, dim1]], dtype=np.int32), 1, o1, from1 or [0] * n, dim1,
+                [m1], None, gpu, sb.FastToSlow, sb.Copy)
+        m0, m1 = [m0], [m1]
     p0 = np.array([[[0] * n, dim0]], dtype=np.int32)
     p1 = np.array([[[0] * n, dim1]], dtype=np.int32)
 
     def go():
-        sb.copy(1, p0, 1, o0, [0] * n, dim0, dim0, [x], None, gpu, p1, 1, o1, from1 or [0] * n, dim1,
-                [y], None, gpu, sb.FastToSlow, sb.Copy)
+        sb.copy(1, p0, 1, o0, [0] * n, dim0, dim0, [x], m0, gpu, p1, 1, o1, from1 or [0] * n, dim1,
+                [y], m1, gpu, sb.FastToSlow, sb.Copy)
     for _ in range(3):
         go()
     sb.sync(gpu)
@@ -50,6 +61,10 @@ C128, C64 = torch.complex128, torch.complex64
 run("plain_c128", "xyztsc", [32, 32, 32, 64, 4, 3], "xyztsc", C128)
 run("perm_cstzyx_c128", "xyztsc", [32, 32, 32, 64, 4, 3], "cstzyx", C128)
 run("perm_cstzyx_c64", "xyztsc", [32, 32, 32, 64, 4, 3], "cstzyx", C64)
+run("perm_cstzyx_f32", "xyztsc", [32, 32, 32, 64, 4, 3], "cstzyx", torch.float32)
+run("perm_cstzyx_f64", "xyztsc", [32, 32, 32, 64, 4, 3], "cstzyx", torch.float64)
+run("masked_perm_cstzyx_c128", "xyztsc", [32, 32, 32, 64, 4, 3], "cstzyx", C128, masked=True)
+run("masked_plain_c128", "xyztsc", [32, 32, 32, 64, 4, 3], "xyztsc", C128, masked=True)
 run("perm_tscxyz_c128", "xyztsc", [32, 32, 32, 64, 4, 3], "tscxyz", C128)
 run("perm_scxyzt_to_xyztsc_c64", "scxyzt", [4, 3, 32, 32, 32, 64], "xyztsc", C64)
 run("perm_tnsxyzc_c128", "xyztscn", [16, 16, 16, 32, 4, 3, 16], "tnsxyzc", C128)

@@ -37,25 +37,50 @@ def go():
             None, gpu, sb.FastToSlow, sb.Copy, comm=comm)
 
 
-for _ in range(3):
-    go()
-sb.sync(gpu)
-torch.cuda.synchronize()
-dist.barrier()
-steps = 10
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-with torch.cuda.stream(stream):
-    e0.record()
-    for _ in range(steps):
-        go()
-    e1.record()
-sb.sync(gpu)
-torch.cuda.synchronize()
-dist.barrier()
-t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
-dist.all_reduce(t, op=dist.ReduceOp.MAX)
+def timed(fn, steps=10):
+    import time
+    for _ in range(3):
+        fn()
+    sb.sync(gpu)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        e0.record()
+        h0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        host_us = (time.perf_counter() - h0) / steps * 1e6  # host time to queue one call
+        e1.record()
+    sb.sync(gpu)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), host_us
+
+
+out = {"world": world,
+       "env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_") or k.startswith("SBB_")}}
+ms, host_us = timed(go)
+out["redistribute_t_to_zt_c64"] = {"ms": ms, "GB/s_per_gpu": 2 * nl * 8 / ms / 1e6, "host_us_per_call": host_us}
+del x, y
+# periodic +1 shifts of a z,t-distributed spin-colour field (BASELINE configs[4]): 64 x 64 x 32 x 32 x (4,3) per GPU
+dimf = [64, 64, 32 * pz, 32 * pt, 4, 3]
+part = sb.basic_partitioning("xyztsc", dimf, [1, 1, pz, pt, 1, 1], "zt", world, 1)
+nf = int(np.prod(part[rank, 1]))
+for es, tag, real in (() if os.environ.get("SBB_ONLY_REDIST") else ((8, "c64", torch.float32), (16, "c128", torch.float64))):
+    fx = torch.view_as_complex(torch.rand(nf, 2, device=dev, dtype=real))
+    fy = torch.zeros_like(fx)
+    for mu, lab in enumerate("xyzt"):
+        shift = [0] * 6
+        shift[mu] = 1
+        ms, host_us = timed(lambda: sb.copy(1, part, 1, "xyztsc", [0] * 6, dimf, dimf, [fx], None, gpu, part, 1,
+                                            "xyztsc", shift, dimf, [fy], None, gpu, sb.FastToSlow, sb.Copy,
+                                            comm=comm))
+        out["shift_%s_%s" % (lab, tag)] = {"ms": ms, "GB/s_per_gpu": 2 * nf * es / ms / 1e6,
+                                           "host_us_per_call": host_us}
+    del fx, fy
 if rank == 0:
-    ms = float(t.item())
-    print(json.dumps({"world": world, "ms": ms, "GB/s_per_gpu": 2 * nl * 8 / ms / 1e6,
-                      "env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_") or k.startswith("SBB_")}}))
+    print(json.dumps(out))
 dist.destroy_process_group()

@@ -240,9 +240,9 @@ int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0
              int co, int copyadd) {
     SBB_TRY({
         Comm *c = (Comm *)comm;
-        bool has_m0 = false, has_m1 = false;
-        for (int i = 0; mask0 && i < ncomponents0; ++i) has_m0 = has_m0 || mask0[i] != nullptr;
-        for (int i = 0; mask1 && i < ncomponents1; ++i) has_m1 = has_m1 || mask1[i] != nullptr;
+        // Whether a copy is masked must not depend on the rank (a rank whose components are all
+        // empty passes null entries): it is decided by the mask ARRAYS being given.
+        const bool has_m0 = mask0 != nullptr, has_m1 = mask1 != nullptr;
         CopyArgs a = make_copy_args(nd0, p0, ncomponents0, o0, from0, size0, dim0, nd1, p1,
                                     ncomponents1, o1, from1, dim1, c ? c->nranks : 1,
                                     c ? c->rank : 0, co, copyadd);

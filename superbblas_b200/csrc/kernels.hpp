@@ -41,6 +41,30 @@ namespace sbb {
                       std::string *describe = nullptr, const float *mask_a = nullptr,
                       const float *mask_b = nullptr);
 
+    /// Peer-memory signalling of an exchange round: `launch_signal` (queued behind the pack kernels)
+    /// stores `seq` into slot `me` of every rank's flag array; `launch_wait` (queued before the unpack
+    /// kernels) spins until all `nranks` slots of this rank's flag array have reached `seq`.
+    void launch_signal(unsigned long long *const *peer_flags, int me, int nranks,
+                       unsigned long long seq, cudaStream_t stream);
+    void launch_wait(const unsigned long long *flags, int nranks, unsigned long long seq,
+                     cudaStream_t stream);
+
+    /// Exchange signal fused into a pack kernel: the last CTA of the kernel to finish stores `sig_seq`
+    /// into slot `me` of every rank's flag array (`done` counts finished CTAs and is left at zero).
+    /// (The wait side stays a one-warp kernel of its own: a persistent, SM-filling unpack kernel
+    /// that spins could keep this rank's next pack kernel off the SMs while the peer does the same.)
+    struct ExchangeSync {
+        unsigned long long *const *peer_flags = nullptr;
+        unsigned long long sig_seq = 0;
+        unsigned *done = nullptr;
+        int nranks = 0, me = 0;
+    };
+    /// Hand `xs` to the next permute kernel launched by permute_copy (single-launch boxes only).
+    void set_exchange_sync(const ExchangeSync *xs);
+    /// True when the last set_exchange_sync was not picked up by a kernel (the caller then launches
+    /// the stand-alone signal / wait kernel); clears it either way.
+    bool exchange_sync_pending();
+
     void set_grid_cap(int ctas);
     int grid_cap();
 

@@ -50,6 +50,17 @@ namespace sbb {
     int grid_cap() { return g_grid_cap; }
 
     namespace {
+        const ExchangeSync *g_xs = nullptr;
+        bool g_xs_blocked = false; // inside a multi-launch box: a signal must not ride on a partial launch
+    }
+    void set_exchange_sync(const ExchangeSync *xs) { g_xs = xs; }
+    bool exchange_sync_pending() {
+        const bool pending = g_xs != nullptr;
+        g_xs = nullptr;
+        return pending;
+    }
+
+    namespace {
 
         constexpr int KD = 8;   // dims handled inside one launch (after merging)
         constexpr int MAXT = 6; // tiled dims
@@ -160,6 +171,67 @@ namespace sbb {
             __device__ __forceinline__ V combine(V, V x) const { return x; }
         };
 
+        // ---- global memory accessors ----------------------------------------------------------------
+        // address = base + 32-bit slot offset x element size in ONE instruction (IMAD.WIDE.U32), then
+        // the memory instruction itself; written in PTX because the compiler otherwise carries every
+        // slot offset as a 64-bit pair and spends 4-5 integer instructions per access, which made the
+        // kernel issue bound for 4- and 8-byte elements (profiles/r1_permute64_ncu.txt).
+        template <typename T>
+        __device__ __forceinline__ unsigned long long elem_addr(const T *base, unsigned off) {
+            unsigned long long a;
+            asm("mad.wide.u32 %0, %1, %2, %3;"
+                : "=l"(a)
+                : "r"(off), "n"((unsigned)sizeof(T)), "l"(base));
+            return a;
+        }
+        /// NC: read-only path (ld.global.nc) for the source; the destination of an Add is read coherently
+        template <bool NC, typename T> __device__ __forceinline__ T ld_elem(const T *base, unsigned off) {
+            static_assert(sizeof(T) == 4 || sizeof(T) == 8 || sizeof(T) == 16, "element size");
+            const unsigned long long a = elem_addr(base, off);
+            T v;
+            if constexpr (sizeof(T) == 4) {
+                unsigned x;
+                if (NC) asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(x) : "l"(a));
+                else asm volatile("ld.global.b32 %0, [%1];" : "=r"(x) : "l"(a));
+                memcpy(&v, &x, 4);
+            } else if constexpr (sizeof(T) == 8) {
+                uint2 x;
+                if (NC) asm volatile("ld.global.nc.v2.b32 {%0,%1}, [%2];" : "=r"(x.x), "=r"(x.y) : "l"(a));
+                else asm volatile("ld.global.v2.b32 {%0,%1}, [%2];" : "=r"(x.x), "=r"(x.y) : "l"(a));
+                memcpy(&v, &x, 8);
+            } else {
+                uint4 x;
+                if (NC)
+                    asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                                 : "l"(a));
+                else
+                    asm volatile("ld.global.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                                 : "l"(a));
+                memcpy(&v, &x, 16);
+            }
+            return v;
+        }
+        template <typename T> __device__ __forceinline__ void st_elem(T *base, unsigned off, const T &v) {
+            static_assert(sizeof(T) == 4 || sizeof(T) == 8 || sizeof(T) == 16, "element size");
+            const unsigned long long a = elem_addr(base, off);
+            if constexpr (sizeof(T) == 4) {
+                unsigned x;
+                memcpy(&x, &v, 4);
+                asm volatile("st.global.b32 [%0], %1;" ::"l"(a), "r"(x));
+            } else if constexpr (sizeof(T) == 8) {
+                uint2 x;
+                memcpy(&x, &v, 8);
+                asm volatile("st.global.v2.b32 [%0], {%1,%2};" ::"l"(a), "r"(x.x), "r"(x.y));
+            } else {
+                uint4 x;
+                memcpy(&x, &v, 16);
+                asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(a), "r"(x.x), "r"(x.y),
+                             "r"(x.z), "r"(x.w));
+            }
+        }
+
         // ---- the kernel -------------------------------------------------------------------------
 
         /// Decompose slot index e following the enumeration `ord` (positions in tdim[]).
@@ -199,14 +271,15 @@ namespace sbb {
         __global__ void __launch_bounds__(NT, MINB)
             permute_kernel(const __grid_constant__ PermParams p, const Tables tab,
                            const typename Op::T *__restrict__ src, typename Op::Q *dst, Op op,
-                           const float *__restrict__ ma, const float *__restrict__ mb) {
+                           const float *__restrict__ ma, const float *__restrict__ mb,
+                           const ExchangeSync xs) {
             using T = typename Op::T;
             using Q = typename Op::Q;
             extern __shared__ __align__(16) unsigned char smem_raw[];
             T *smem = reinterpret_cast<T *>(smem_raw);
 
             const unsigned tid = threadIdx.x;
-            if (blockIdx.x >= p.ntiles) return;
+            if (blockIdx.x >= p.ntiles) return; // (never taken: the grid is at most ntiles)
 
             // ---- per-slot maps: tile invariant, kept in registers ---------------------------------
             unsigned so[EPT], dof[EPT], sp[EPT];
@@ -287,7 +360,7 @@ namespace sbb {
                 const T *s = src + t.sbase;
 #pragma unroll
                 for (int k = 0; k < EPT; ++k)
-                    if (t.mask_l >> k & 1) r[k] = s[so[k]];
+                    if (t.mask_l >> k & 1) r[k] = ld_elem<true>(s, so[k]);
             };
 
             const unsigned G = gridDim.x;
@@ -295,8 +368,23 @@ namespace sbb {
             unsigned tile = blockIdx.x;
             longlong2 e_nxt = my_tiles > 1 ? tab.tiles[tile + G] : tab.tiles[tile];
             Tile cur = make_tile(tab.tiles[tile], tile);
+            // Masks travel like the data: the mask words of tile i+1 are requested together with its
+            // source elements, and turned into store predicates when tile i+1 becomes current.
+            float fa[MASK ? EPT : 1], fb[MASK ? EPT : 1];
+            auto load_masks = [&](const Tile &t) {
+                if (!MASK) return;
+#pragma unroll
+                for (int k = 0; k < (MASK ? EPT : 1); ++k) {
+                    fa[k] = fb[k] = 1.0f;
+                    if (t.mask_s >> k & 1) {
+                        if (ma) fa[k] = ld_elem<true>(ma + t.dbase, dof[k]);
+                        if (mb) fb[k] = ld_elem<true>(mb + t.dbase, dof[k]);
+                    }
+                }
+            };
             T r[EPT];
             load(cur, r);
+            load_masks(cur);
             for (unsigned i = 0; i < my_tiles; ++i, tile += G) {
                 const bool has_next = i + 1 < my_tiles;
                 const longlong2 e_nn = i + 2 < my_tiles ? tab.tiles[tile + 2 * G] : e_nxt;
@@ -305,17 +393,8 @@ namespace sbb {
                 Q *w = dst + cur.dbase;
                 if (MASK) {
                     // masked-out destination elements are left untouched
-                    float fa[EPT], fb[EPT];
 #pragma unroll
-                    for (int k = 0; k < EPT; ++k) {
-                        fa[k] = fb[k] = 1.0f;
-                        if (cur.mask_s >> k & 1) {
-                            if (ma) fa[k] = ma[cur.dbase + dof[k]];
-                            if (mb) fb[k] = mb[cur.dbase + dof[k]];
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < EPT; ++k)
+                    for (int k = 0; k < (MASK ? EPT : 1); ++k)
                         if (fa[k] == 0.0f || fb[k] == 0.0f) cur.mask_s &= ~(1u << k);
                 }
                 if (SMEM) {
@@ -323,43 +402,63 @@ namespace sbb {
                     for (int k = 0; k < EPT; ++k)
                         if (cur.mask_l >> k & 1) smem[sp[k] >> 16] = r[k];
                     __syncthreads();
-                    if (has_next) load(nxt, r); // in flight during the store phase
+                    if (has_next) load(nxt, r), load_masks(nxt); // in flight during the store phase
                     if (op.add()) {
                         Q o[EPT];
 #pragma unroll
                         for (int k = 0; k < EPT; ++k)
-                            if (cur.mask_s >> k & 1) o[k] = w[dof[k]];
+                            if (cur.mask_s >> k & 1) o[k] = ld_elem<false>(w, dof[k]);
 #pragma unroll
                         for (int k = 0; k < EPT; ++k)
                             if (cur.mask_s >> k & 1)
-                                w[dof[k]] = op.combine(o[k], smem[sp[k] & 0xffffu]);
+                                st_elem(w, dof[k], op.combine(o[k], smem[sp[k] & 0xffffu]));
                     } else {
 #pragma unroll
                         for (int k = 0; k < EPT; ++k)
-                            if (cur.mask_s >> k & 1) w[dof[k]] = op.apply(smem[sp[k] & 0xffffu]);
+                            if (cur.mask_s >> k & 1) st_elem(w, dof[k], op.apply(smem[sp[k] & 0xffffu]));
                     }
                     __syncthreads();
                 } else {
                     T r2[EPT];
-                    if (has_next) load(nxt, r2);
+                    if (has_next) load(nxt, r2), load_masks(nxt);
                     if (op.add()) {
                         Q o[EPT];
 #pragma unroll
                         for (int k = 0; k < EPT; ++k)
-                            if (cur.mask_s >> k & 1) o[k] = w[dof[k]];
+                            if (cur.mask_s >> k & 1) o[k] = ld_elem<false>(w, dof[k]);
 #pragma unroll
                         for (int k = 0; k < EPT; ++k)
-                            if (cur.mask_s >> k & 1) w[dof[k]] = op.combine(o[k], r[k]);
+                            if (cur.mask_s >> k & 1) st_elem(w, dof[k], op.combine(o[k], r[k]));
                     } else {
 #pragma unroll
                         for (int k = 0; k < EPT; ++k)
-                            if (cur.mask_s >> k & 1) w[dof[k]] = op.apply(r[k]);
+                            if (cur.mask_s >> k & 1) st_elem(w, dof[k], op.apply(r[k]));
                     }
 #pragma unroll
                     for (int k = 0; k < EPT; ++k) r[k] = r2[k];
                 }
                 cur = nxt;
                 e_nxt = e_nn;
+            }
+
+            // Pack side of an exchange: when the last CTA of this kernel has finished, all its stores
+            // (which went to the receivers' arenas over NVLink) are complete: raise this rank's flag
+            // at every receiver (fused signal: no kernel boundary, no NCCL barrier)
+            if (xs.peer_flags) {
+                __threadfence_system();
+                __syncthreads();
+                if (tid == 0) {
+                    const unsigned prev = atomicAdd(xs.done, 1u);
+                    if (prev + 1 == gridDim.x) {
+                        __threadfence_system();
+                        atomicExch(xs.done, 0u); // the next user is ordered behind this kernel
+                        for (int q = 0; q < xs.nranks; ++q) {
+                            unsigned long long *f = xs.peer_flags[q] + xs.me;
+                            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(xs.sig_seq)
+                                         : "memory");
+                        }
+                    }
+                }
             }
         }
 
@@ -780,18 +879,22 @@ namespace sbb {
                 unsigned grid = (unsigned)std::min<int64_t>(
                     lp.p.ntiles, (int64_t)dev_info(device).sms * it->second);
                 if (grid_cap() > 0) grid = std::min<unsigned>(grid, (unsigned)grid_cap());
+                ExchangeSync xs;
+                if (g_xs && !(g_xs_blocked && g_xs->peer_flags)) xs = *g_xs, g_xs = nullptr;
                 {
                     KernelTimer timer("permute", stream);
                     kernel<<<grid, NT, smem_bytes, stream>>>(lp.p, lp.tab, (const T *)src, (Q *)dst, op,
-                                                             ma, mb);
+                                                             ma, mb, xs);
                 }
                 count_launch();
                 cuda_check(cudaGetLastError(), "permute_kernel launch");
             };
+            // small elements: three resident CTAs per SM (more loads in flight per SM for the same bytes)
+            constexpr int MINB = (sizeof(T) <= 8 && sizeof(Q) <= 8 && EPT_ <= 8 && !MASK) ? 3 : 2;
             if (lp.smem)
-                go(permute_kernel<Op, true, EPT_, 2, MASK>);
+                go(permute_kernel<Op, true, EPT_, MINB, MASK>);
             else
-                go(permute_kernel<Op, false, EPT_, 2, MASK>);
+                go(permute_kernel<Op, false, EPT_, MINB, MASK>);
         }
 
         template <class V>
@@ -804,7 +907,22 @@ namespace sbb {
             cuda_check(cudaGetLastError(), "zero_kernel launch");
         }
 
-        int max_tile_for(int) { return NT * EPT; }
+        /// Slots per thread of the raw-move kernels: 4- and 8-byte elements get 16 when the tile is
+        /// transposed through shared memory (a tile must hold runs of >= 256 B on both sides and
+        /// enough bytes in flight; measured +17 % for float, +7 % for 8-byte transposes), 8 otherwise
+        /// (the direct variant double-buffers in registers); SBB_EPT4 / SBB_EPT8 override (8 or 16)
+        int ept_for(int es) {
+            static int e4 = -1, e8 = -1;
+            if (e4 < 0) {
+                const char *a = std::getenv("SBB_EPT4"), *b = std::getenv("SBB_EPT8");
+                e4 = a ? std::atoi(a) : 16;
+                e8 = b ? std::atoi(b) : 16;
+            }
+            if (es == 4) return e4 == 8 ? 8 : 16;
+            if (es == 8) return e8 == 16 ? 16 : 8;
+            return EPT;
+        }
+        int max_tile_for(int es) { return NT * ept_for(es); }
 
         /// Widen the element when the fastest dim is shared, contiguous and aligned
         int promote(Canon &c, int es, const void *src, const void *dst, bool has_src) {
@@ -960,6 +1078,7 @@ namespace sbb {
                 } else {
                     es = promote(c, dtype_size(dt0), src, dst, true);
                     lp = plan_launch(c, es, max_tile_for(es), true);
+                    if (!lp.smem && lp.p.tile_elems > NT * EPT) lp = plan_launch(c, es, NT * EPT, true);
                     if (!describe) {
                         build_tables(lp, true, device, stream);
                         remember(c, lp, es);
@@ -975,8 +1094,11 @@ namespace sbb {
                 }
                 const char *s = (const char *)src + c.soff * es;
                 char *d = (char *)dst + c.doff * es;
+                const bool wide = lp.p.tile_elems > NT * EPT; // planned with 16 slots per thread
                 if (es == 16) launch_perm<MoveOp<uint4>>(lp, s, d, {}, device, stream);
+                else if (es == 8 && wide) launch_perm<MoveOp<uint2>, false, 16>(lp, s, d, {}, device, stream);
                 else if (es == 8) launch_perm<MoveOp<uint2>>(lp, s, d, {}, device, stream);
+                else if (wide) launch_perm<MoveOp<unsigned>, false, 16>(lp, s, d, {}, device, stream);
                 else launch_perm<MoveOp<unsigned>>(lp, s, d, {}, device, stream);
                 return;
             }
@@ -1023,6 +1145,48 @@ namespace sbb {
 
     } // namespace
 
+    // ---- peer-memory signalling (the "barrier" of an exchange, without NCCL on the data path) ---------
+    namespace {
+        /// After the pack kernels of a round (same stream, so their stores -- including the ones that
+        /// went to peer memory over NVLink -- are complete): raise my flag in every rank's arena.
+        __global__ void signal_kernel(unsigned long long *const *peer_flags, int me, int nranks,
+                                      unsigned long long seq) {
+            const int q = threadIdx.x;
+            if (q < nranks) {
+                unsigned long long *f = peer_flags[q] + me;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
+            }
+        }
+        /// Before the unpack kernels of a round: wait until every rank has raised its flag to `seq`
+        __global__ void wait_kernel(const unsigned long long *flags, int nranks, unsigned long long seq) {
+            const int r = threadIdx.x;
+            if (r < nranks) {
+                unsigned long long v;
+                for (;;) { // relaxed polling (served by L2, where the peers' stores land); one fence at the end
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+                    if (v >= seq) break;
+                    __nanosleep(100);
+                }
+            }
+            __syncthreads();
+            __threadfence_system();
+        }
+    }
+
+    void launch_signal(unsigned long long *const *peer_flags, int me, int nranks,
+                       unsigned long long seq, cudaStream_t stream) {
+        signal_kernel<<<1, std::max(32, (nranks + 31) / 32 * 32), 0, stream>>>(peer_flags, me, nranks, seq);
+        count_launch();
+        cuda_check(cudaGetLastError(), "signal_kernel launch");
+    }
+
+    void launch_wait(const unsigned long long *flags, int nranks, unsigned long long seq,
+                     cudaStream_t stream) {
+        wait_kernel<<<1, std::max(32, (nranks + 31) / 32 * 32), 0, stream>>>(flags, nranks, seq);
+        count_launch();
+        cuda_check(cudaGetLastError(), "wait_kernel launch");
+    }
+
     void permute_cache_clear() {
         for (auto &kv : prepared_cache()) {
             LaunchPlan &lp = kv.second.lp;
@@ -1053,6 +1217,10 @@ namespace sbb {
             return;
         }
         // More than KD irreducible dims: iterate over the slowest ones on the host
+        struct Block {
+            Block() { g_xs_blocked = true; }
+            ~Block() { g_xs_blocked = false; }
+        } block;
         const int outer = c.nd - KD;
         std::vector<int> idx(outer, 0);
         for (;;) {

@@ -309,8 +309,12 @@ namespace sbb {
             agree_min(c, 1);
             release_arena(c);
             half_bytes = (half_bytes + half_bytes / 4 + (1 << 20) - 1) >> 20 << 20; // grow with slack
-            int ok = cudaMalloc((void **)&c->arena, 2 * half_bytes) == cudaSuccess ? 1 : 0;
+            // [half 0 | half 1 | one 64-bit flag per rank]
+            const size_t flag_bytes = ((size_t)c->nranks * sizeof(unsigned long long) + 255) / 256 * 256;
+            int ok = cudaMalloc((void **)&c->arena, 2 * half_bytes + flag_bytes) == cudaSuccess ? 1 : 0;
             if (!ok) cudaGetLastError(), c->arena = nullptr;
+            if (ok) // flags start at zero (sequence numbers only grow); queued before the handles leave
+                cuda_check(cudaMemsetAsync(c->arena + 2 * half_bytes, 0, flag_bytes, d.comm_stream), "memset");
             cudaIpcMemHandle_t mine;
             std::memset(&mine, 0, sizeof mine);
             if (ok && cudaIpcGetMemHandle(&mine, c->arena) != cudaSuccess) cudaGetLastError(), ok = 0;
@@ -344,6 +348,15 @@ namespace sbb {
                 return;
             }
             c->half_bytes = half_bytes;
+            c->flags = (unsigned long long *)(c->arena + 2 * half_bytes);
+            std::vector<unsigned long long *> pf(c->nranks);
+            for (int r = 0; r < c->nranks; ++r) pf[r] = (unsigned long long *)(c->peer[r] + 2 * half_bytes);
+            if (!c->peer_flags)
+                cuda_check(cudaMalloc((void **)&c->peer_flags, sizeof(void *) * c->nranks), "cudaMalloc");
+            cuda_check(cudaMemcpyAsync(c->peer_flags, pf.data(), sizeof(void *) * c->nranks,
+                                       cudaMemcpyHostToDevice, d.comm_stream), "memcpy");
+            cuda_check(cudaStreamSynchronize(d.comm_stream), "cudaStreamSynchronize");
+            agree_min(c, 1); // nobody signals before every rank's flags are zeroed and mapped
         }
     }
 
@@ -358,10 +371,13 @@ namespace sbb {
             std::memcpy(id.bytes, id128, 128);
             nccl_check(nccl().CommInitRank(&c->nccl, nranks, id, rank), "ncclCommInitRank");
             cuda_check(cudaMalloc((void **)&c->flag, 256), "cudaMalloc");
+            cuda_check(cudaMemset(c->flag, 0, 256), "cudaMemset");
             const char *e = std::getenv("SBB_P2P");
             c->p2p = !(e && std::atoi(e) == 0);
             // every rank must take the same decision
             c->p2p = agree_min(c, c->p2p ? 1 : 0) != 0;
+            const char *sg = std::getenv("SBB_P2P_SIGNAL");
+            c->signal = agree_min(c, (sg && std::atoi(sg) == 0) ? 0 : 1) != 0;
         }
         return c;
     }
@@ -374,6 +390,7 @@ namespace sbb {
             cudaStreamSynchronize(device_state(c->device).comm_stream);
             release_arena(c);
             if (c->flag) cudaFree(c->flag);
+            if (c->peer_flags) cudaFree(c->peer_flags);
             nccl().CommDestroy(c->nccl);
         }
         delete c;
@@ -444,6 +461,7 @@ namespace sbb {
                       const double *alpha, const std::vector<Buffer> &v0,
                       const std::vector<Buffer> &v1, Comm *comm,
                       const std::vector<Buffer> *mask_a, const std::vector<Buffer> *mask_b) {
+        set_exchange_sync(nullptr); // nothing left over from a call that ended with an exception
         // a rank without work still takes part in the barrier of the peer-memory transport
         if (plan.ops.empty() && !(comm && comm->nccl && comm->p2p && plan.any_comm)) return;
         const int es0 = dtype_bytes(dtype0), es1 = dtype_bytes(dtype1);
@@ -590,6 +608,27 @@ namespace sbb {
             if (seg_recv[plan.nranks]) recvbuf = (char *)pool_alloc(home, seg_recv[plan.nranks]);
         }
 
+        // Optional DMA variant of the peer-memory exchange (SBB_P2P_DMA_MB = message size in MB from
+        // which it is used; default 0 = never): the pack kernels fill a local send buffer at HBM speed
+        // and a copy engine pushes every round's window into the receiver's arena.  Measured on this
+        // pool's B200 pairs it is SLOWER than stores issued by the pack kernels themselves (3.9 ms vs
+        // 2.6 ms for the 2-GPU redistribution of config 3: the copy engine moves ~220 GB/s per
+        // direction, the kernels' stores ~310 GB/s), so it stays off; kept for boxes where the balance
+        // differs.  All ranks take the same decision (max_pair_elems is a property of the exchange).
+        bool dma = false;
+        if (use_p2p) {
+            static long long thr = -1;
+            if (thr < 0) {
+                const char *e = std::getenv("SBB_P2P_DMA_MB");
+                thr = (e ? std::atoll(e) : 0) << 20;
+            }
+            dma = thr > 0 && plan.max_pair_elems * (int64_t)esw >= thr;
+            if (dma) {
+                for (int r = 0; r < plan.nranks; ++r)
+                    seg_send[r + 1] = seg_send[r] + ((size_t)plan.send_elems[r] * esw + 255) / 256 * 256;
+                if (seg_send[plan.nranks]) sendbuf = (char *)pool_alloc(home, seg_send[plan.nranks]);
+            }
+        }
         std::vector<char *> p2p_send_base(plan.nranks, nullptr), p2p_recv_base(plan.nranks, nullptr);
         if (use_p2p) {
             const size_t half = (comm->epoch & 1) * comm->half_bytes;
@@ -607,7 +646,22 @@ namespace sbb {
         auto stream_for = [&](int dev) {
             return use_aux && dev == home ? hs.aux_stream : device_state(dev).stream;
         };
+        // While an exchange is in flight the kernels on the auxiliary stream (local part, unpack) run
+        // on a reduced grid (aux_grid CTAs, 0 = no limit): they are persistent, and at full width
+        // they would hold every SM until they end, so that the pack kernels of the next round could
+        // not start beside them.
+        int aux_grid = 0;
         auto run = [&](const BoxOp &op) {
+            struct CapGuard {
+                int saved;
+                bool on;
+                CapGuard(bool on_, int cap) : saved(grid_cap()), on(on_) {
+                    if (on) set_grid_cap(cap);
+                }
+                ~CapGuard() {
+                    if (on) set_grid_cap(saved);
+                }
+            } guard(use_aux && aux_grid > 0 && op.kind != BoxOp::Pack, aux_grid);
             sbk_box_desc desc = to_desc(op);
             switch (op.kind) {
             case BoxOp::Local: {
@@ -626,7 +680,7 @@ namespace sbb {
                 desc.soff = op.soff, desc.doff = op.doff;
                 // scaled (and normally converted) before it leaves; with the peer-memory transport
                 // the kernel's stores go straight into the receiver's arena over NVLink
-                char *to = use_p2p ? p2p_send_base[op.peer] : sendbuf + seg_send[op.peer];
+                char *to = use_p2p && !dma ? p2p_send_base[op.peer] : sendbuf + seg_send[op.peer];
                 permute_copy(desc, a.ptr, dtype0, to, wire_dtype, alpha, false, home, hs.stream);
                 break;
             }
@@ -689,28 +743,113 @@ namespace sbb {
                 const char *e = std::getenv("SBB_P2P_PACK_GRID");
                 pack_grid = e ? std::atoi(e) : 74; // measured best on 2 and 4 GPUs (24..296 tried)
             }
+            {
+                static int v = -1;
+                if (v < 0) {
+                    const char *e = std::getenv("SBB_P2P_AUX_GRID");
+                    v = e ? std::atoi(e) : 222; // measured on 2 GPUs: 0 (no limit) 3.18 ms, 148 2.69, 222 2.57
+                }
+                // only worth it when there are several rounds of NVLink-bound packs to overlap with
+                aux_grid = (nrounds > 1 && !dma) ? v : 0;
+            }
             std::vector<cudaEvent_t> &evs = round_events(home, 2 * nrounds);
             use_device(home);
             cuda_check(cudaEventRecord(hs.ev_a, hs.stream), "cudaEventRecord");
             cuda_check(cudaStreamWaitEvent(hs.aux_stream, hs.ev_a, 0), "cudaStreamWaitEvent");
             use_aux = true;
-            if (!args.add)
-                for (const auto &op : plan.ops)
-                    if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
+            // Queue order matters: the (persistent) kernels of the local part fill every SM, so the pack
+            // kernels of round 0 and their signal are queued first; the local part follows on the
+            // auxiliary stream and runs beside them.
+            const bool sig = comm->signal;
+            const unsigned long long seq0 = comm->seq;
+            if (sig) comm->seq += (unsigned long long)nrounds;
+            bool local_done = args.add;
+            // byte window of every (round, peer) of what this rank sends: [lo, hi)
+            std::vector<std::vector<int64_t>> wlo, whi;
+            if (dma) {
+                wlo.assign(nrounds, std::vector<int64_t>(plan.nranks, -1)), whi = wlo;
+                for (const auto &op : plan.ops) {
+                    if (op.kind != BoxOp::Pack) continue;
+                    const int k = round_of(op);
+                    const int64_t b0 = op.doff * esw, b1 = b0 + op.volume() * esw;
+                    auto &lo = wlo[k][op.peer];
+                    auto &hi = whi[k][op.peer];
+                    lo = lo < 0 ? b0 : std::min(lo, b0);
+                    hi = std::max(hi, b1);
+                }
+            }
+            static int fuse_signal = -1;
+            if (fuse_signal < 0) {
+                const char *e = std::getenv("SBB_P2P_FUSED_SIGNAL");
+                fuse_signal = e ? std::atoi(e) : 1;
+            }
             for (int k = 0; k < nrounds; ++k) {
-                set_grid_cap(pack_grid);
+                set_grid_cap(dma ? 0 : pack_grid);
+                // the signal of the round rides on its last pack kernel (raised by the last CTA to finish)
+                const BoxOp *last_pack = nullptr;
                 for (const auto &op : plan.ops)
-                    if (op.kind == BoxOp::Pack && round_of(op) == k) run(op);
+                    if (op.kind == BoxOp::Pack && round_of(op) == k) last_pack = &op;
+                ExchangeSync xs;
+                xs.peer_flags = comm->peer_flags, xs.sig_seq = seq0 + k + 1;
+                xs.done = (unsigned *)comm->flag + 32, xs.nranks = comm->nranks, xs.me = comm->rank;
+                bool signalled = false;
+                for (const auto &op : plan.ops)
+                    if (op.kind == BoxOp::Pack && round_of(op) == k) {
+                        const bool fuse = sig && !dma && fuse_signal && &op == last_pack;
+                        if (fuse) set_exchange_sync(&xs);
+                        run(op);
+                        if (fuse) signalled = !exchange_sync_pending();
+                    }
                 set_grid_cap(0);
                 use_device(home);
-                cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
-                cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
-                nccl_check(nccl().AllReduce(comm->flag, comm->flag + 8, 1, kNcclInt32, kNcclSum,
-                                            comm->nccl, hs.comm_stream),
-                           "ncclAllReduce (barrier)");
-                cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
+                if (dma) {
+                    // push this round's windows with the copy engines, then signal / barrier behind them
+                    cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
+                    cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
+                    for (int r = 0; r < plan.nranks; ++r)
+                        if (wlo[k][r] >= 0)
+                            cuda_check(cudaMemcpyAsync(p2p_send_base[r] + wlo[k][r],
+                                                       sendbuf + seg_send[r] + wlo[k][r],
+                                                       (size_t)(whi[k][r] - wlo[k][r]),
+                                                       cudaMemcpyDeviceToDevice, hs.comm_stream),
+                                       "cudaMemcpyAsync (peer)");
+                    if (sig) {
+                        launch_signal(comm->peer_flags, comm->rank, comm->nranks, seq0 + k + 1,
+                                      hs.comm_stream);
+                    } else {
+                        nccl_check(nccl().AllReduce(comm->flag, comm->flag + 8, 1, kNcclInt32, kNcclSum,
+                                                    comm->nccl, hs.comm_stream),
+                                   "ncclAllReduce (barrier)");
+                    }
+                    cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
+                } else if (sig) {
+                    // my stores of this round are complete (stream order): tell every rank
+                    if (!signalled)
+                        launch_signal(comm->peer_flags, comm->rank, comm->nranks, seq0 + k + 1, hs.stream);
+                } else {
+                    cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
+                    cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
+                    nccl_check(nccl().AllReduce(comm->flag, comm->flag + 8, 1, kNcclInt32, kNcclSum,
+                                                comm->nccl, hs.comm_stream),
+                               "ncclAllReduce (barrier)");
+                    cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
+                }
+                if (!local_done) {
+                    for (const auto &op : plan.ops)
+                        if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
+                    local_done = true;
+                }
             }
             auto wait_round = [&](int k) {
+                if (sig) {
+                    // every rank's stores of round k have landed in my arena once all flags reached
+                    // seq.  The (one-warp) wait kernel spins on the communication stream, beside the
+                    // local part, so that the unpack kernels only wait for an event that is normally
+                    // already complete when the auxiliary stream gets there.
+                    use_device(home);
+                    launch_wait(comm->flags, comm->nranks, seq0 + k + 1, hs.comm_stream);
+                    cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
+                }
                 for (int a : devs) {
                     use_device(a);
                     cuda_check(cudaStreamWaitEvent(stream_for(a), evs[2 * k + 1], 0), "cudaStreamWaitEvent");
@@ -727,11 +866,13 @@ namespace sbb {
                         if (op.kind == BoxOp::Unpack && round_of(op) == k) run(op);
                 }
             }
-            // the compute stream continues after everything of this call (also what makes the
-            // alternation of the arena halves safe)
+            // the compute stream continues after everything of this call: every rank has then seen
+            // every other rank's last signal of this call, which is what makes the alternation of the
+            // arena halves safe (a rank packs call e+1 only after all ranks finished unpacking call e-1)
             use_device(home);
             cuda_check(cudaEventRecord(hs.ev_c, hs.aux_stream), "cudaEventRecord");
             cuda_check(cudaStreamWaitEvent(hs.stream, hs.ev_c, 0), "cudaStreamWaitEvent");
+            // (with DMA also: the send buffer returns to the pool only after the last transfer)
             cuda_check(cudaStreamWaitEvent(hs.stream, evs[2 * nrounds - 1], 0), "cudaStreamWaitEvent");
             use_aux = false;
         } else if (plan.needs_comm) {

@@ -43,6 +43,13 @@ namespace sbb {
         std::vector<char *> peer;  ///< every rank's arena as mapped here (peer[rank] == arena)
         unsigned long long epoch = 0;
         int *flag = nullptr;       ///< device scratch for the barrier / handle exchange
+        // Flag-based signalling (replaces the NCCL all-reduce barrier on the data path): every
+        // arena ends with one 64-bit slot per rank; a sender raises its slot in every receiver's
+        // arena to the sequence number of the round once its pack kernels are done.
+        bool signal = true;                      ///< SBB_P2P_SIGNAL=0 selects the NCCL barrier instead
+        unsigned long long seq = 0;              ///< rounds signalled so far (all ranks agree)
+        unsigned long long *flags = nullptr;     ///< my slots (inside my arena allocation)
+        unsigned long long **peer_flags = nullptr; ///< device array: every rank's slots as mapped here
     };
 
     void nccl_unique_id(void *id128);

@@ -67,6 +67,8 @@ def main():
     rng = np.random.default_rng(4242)  # the same sequence on every rank
     bad = 0
     for it in range(args.cases):
+        if rank == 0 and os.environ.get("SBB_DIST_VERBOSE"):
+            print("copy case %d" % it, flush=True)
         nc0, nc1 = int(rng.integers(1, 3)), int(rng.integers(1, 3))
         case = C.random_copy_case(rng, nparts0=world * nc0, nparts1=world * nc1)
         masked = it % 3 == 2  # every third case carries (compatible) masks on both tensors

@@ -1,6 +1,7 @@
 """N>1 path.  CPU: world_size 2 and 3 with the gloo backend (host logic: plans, message layout,
 ordering).  GPU: world_size = number of devices (>= 2) with NCCL inside the library."""
 import os
+import signal
 import subprocess
 import sys
 
@@ -9,15 +10,23 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def launch(n, backend, cases, port):
+def launch(n, backend, cases, port, timeout=600):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "dist_check.py"), "--backend", backend, "--cases", str(cases)]
     # tiny pipeline pieces so that the cutting of remote boxes is exercised by the small test cases
     env = dict(os.environ, OMP_NUM_THREADS="1", SBB_CHUNK_BYTES="256")
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
-    out = r.stdout + r.stderr
-    assert r.returncode == 0, out[-3000:]
+    # own session, so that a hang can be ended together with every worker process (a worker left
+    # spinning on a GPU would disturb whatever runs next)
+    proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env,
+                            cwd=ROOT, start_new_session=True)
+    try:
+        out, _ = proc.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, _ = proc.communicate()
+        raise AssertionError("multi-rank check timed out after %d s:\n%s" % (timeout, out[-3000:]))
+    assert proc.returncode == 0, out[-3000:]
     assert "failures=0" in out, out[-3000:]
 
 
@@ -32,4 +41,4 @@ def test_nccl_world():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
-    launch(min(n, 8), "nccl", 20, 29531)
+    launch(min(n, 8), "nccl", 20, 29531, timeout=300)
