@@ -383,10 +383,16 @@ def main():
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
         try:
-            c = cpu_contraction_sample(3, 1)
-            cpu_baseline = {"value": c["flop_per_step"] * c["steps"] / c["total_s"] / 1e12,
-                            "unit": "TFLOP/s", "cores": c["cores"], "kind": c["kind"],
-                            "sample": c["sample"]}
+            # in a process of its own (the reference arm of this script): inside this process two
+            # OpenMP runtimes (torch's and the reference library's) fight over the cores and the
+            # same sample runs 3x slower
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference",
+                                  "--steps", "3", "--warmup", "1"], capture_output=True, text=True,
+                                 timeout=600).stdout
+            ref = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+            if "unavailable" in ref:
+                raise RuntimeError(ref["unavailable"])
+            cpu_baseline = ref["cpu_baseline"]
         except Exception as e:  # noqa: BLE001
             cpu_baseline = {"value": None, "unit": "TFLOP/s", "cores": os.cpu_count(),
                             "kind": "reference", "sample": "unavailable: %s" % e}
@@ -435,9 +441,10 @@ def reshuffle_extras(sb, torch, dist, dev, gpu, stream, comm, rank, world, timed
                                                 if nbytes_elem == 8 else torch.float64))
 
     def record(name, nbytes, fn, steps=20):
-        sb.profile_enable(True)
+        ms = timed(fn, steps, 3)  # the throughput figure: no per-kernel events in the stream
+        sb.profile_enable(True)   # second pass: the copy kernels alone, bracketed by events
         sb.profile_read("permute")
-        ms = timed(fn, steps, 3)
+        timed(fn, steps, 1)
         kms, kn = sb.profile_read("permute")
         sb.profile_enable(False)
         gbs = nbytes * world * steps / (ms * 1e-3) / 1e9
