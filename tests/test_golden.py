@@ -17,9 +17,11 @@ def load_golden():
         z = np.load(f, allow_pickle=True)
         case = z["case"].item()
         g = dict(kind=str(z["kind"]), case=case)
-        if g["kind"] == "copy":
+        if g["kind"] in ("copy", "masked_copy"):
             g["v0"], g["v1"] = C.make_copy_data(case, int(z["seed"]), consistent=True)
             g["want"] = [z["want_%d" % j] for j in range(len(g["v1"]))]
+            g["m0"], g["m1"] = C.make_masks(case, int(z["seed"])) if g["kind"] == "masked_copy" \
+                else (None, None)
         else:
             g["v0"], g["v1"], g["vr"] = C.make_contraction_data(case, int(z["seed"]))
             g["want"] = [z["want_%d" % j] for j in range(len(g["vr"]))]
@@ -28,14 +30,14 @@ def load_golden():
 
 
 def test_golden_files_exist():
-    assert len(load_golden()) >= 20
+    assert len(load_golden()) >= 40
 
 
 def test_oracle_reproduces_golden_vectors():
     for name, g in load_golden():
         case = g["case"]
-        if g["kind"] == "copy":
-            got = C.oracle_copy(case, g["v0"], g["v1"])
+        if g["kind"] in ("copy", "masked_copy"):
+            got = C.oracle_copy(case, g["v0"], g["v1"], g["m0"], g["m1"])
             for j, (x, w) in enumerate(zip(got, g["want"])):
                 assert C.bits_equal(x, w), (name, j)
         else:

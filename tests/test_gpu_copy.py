@@ -242,9 +242,9 @@ def test_golden_vectors_on_gpu(gu):
     """Outputs of the real reference (tests/golden/*.npz) reproduced by the CUDA path."""
     from tests.test_golden import load_golden
     for name, g in load_golden():
-        if g["kind"] != "copy":
+        if g["kind"] not in ("copy", "masked_copy"):
             continue
-        got = gu.run_copy(g["case"], g["v0"], g["v1"])
+        got = gu.run_copy(g["case"], g["v0"], g["v1"], mask0=g["m0"], mask1=g["m1"])
         for j, (x, w) in enumerate(zip(got, g["want"])):
             assert C.bits_equal(x, w), (name, j)
 
