@@ -36,6 +36,7 @@
 #include "superbblas_b200.h"
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <complex>
 #include <cstring>
 #include <functional>
@@ -165,8 +166,16 @@ namespace superbblas {
                 });
             }
             T *data() const { return ptr.get(); }
+            T *begin() const { return ptr.get(); }
+            T *end() const { return ptr.get() + n; }
             std::size_t size() const { return n; }
             XPU ctx() const { return xpu; }
+            /// Element access (meaningful for host vectors only, as in the reference)
+            T &operator[](std::size_t i) const { return ptr.get()[i]; }
+            void clear() {
+                n = 0;
+                ptr.reset();
+            }
 
         private:
             template <typename U> static U *superbblas_b200_alloc(std::size_t n, Context c) {
@@ -247,6 +256,143 @@ namespace superbblas {
     }
     template <typename T> void deallocate(T *ptr, Context ctx) {
         detail::check(sbb_deallocate(detail::ctx_ptr(&ctx), (void *)ptr));
+    }
+
+    // ---- helpers of namespace detail that the reference's own tests/dist.cpp uses ----------------------
+    namespace detail {
+        /// Lists of ranges (reference: dist.h:36-51)
+        template <std::size_t N> using From_size_item = PartitionItem<N>;
+        template <std::size_t N> using From_size = std::vector<PartitionItem<N>>;
+
+        /// Total number of sites of a list of ranges
+        template <std::size_t N> std::size_t volume(const From_size<N> &fs) {
+            std::size_t v = 0;
+            for (const auto &it : fs) v += volume<N>(it[1]);
+            return v;
+        }
+
+        /// Intersection of two ranges on a periodic lattice, as a list of plain ranges (semantics of
+        /// the reference's dist.h:353-495; written from the definition: a site belongs to a range
+        /// iff (site - from) mod dim < size).  Per dimension the common sites form at most two runs.
+        template <std::size_t N>
+        From_size<N> intersection(const Coor<N> &from0, const Coor<N> &size0, const Coor<N> &from1,
+                                  const Coor<N> &size1, const Coor<N> &dim) {
+            std::array<std::vector<std::array<int, 2>>, N> runs; // per dimension: {first site, length}
+            for (std::size_t k = 0; k < N; ++k) {
+                const int d = dim[k];
+                if (d <= 0) return {};
+                auto inside = [&](int site, int from, int size) {
+                    return ((site - from) % d + d) % d < size;
+                };
+                std::vector<char> in((std::size_t)d);
+                bool all = true, any = false;
+                for (int i = 0; i < d; ++i) {
+                    in[i] = inside(i, from0[k], size0[k]) && inside(i, from1[k], size1[k]);
+                    all = all && in[i];
+                    any = any || in[i];
+                }
+                if (!any) return {};
+                if (all) {
+                    runs[k].push_back({((from0[k] % d) + d) % d, d});
+                    continue;
+                }
+                // start at a site that is outside, so that no run wraps around the scan
+                int start = 0;
+                while (in[start]) ++start;
+                for (int j = 1; j <= d;) {
+                    const int i = (start + j) % d;
+                    if (!in[i]) {
+                        ++j;
+                        continue;
+                    }
+                    int len = 0;
+                    while (j + len <= d && in[(start + j + len) % d]) ++len;
+                    runs[k].push_back({i, len});
+                    j += len;
+                }
+            }
+            From_size<N> r(1);
+            for (std::size_t k = 0; k < N; ++k) {
+                From_size<N> next;
+                for (const auto &box : r)
+                    for (const auto &run : runs[k]) {
+                        PartitionItem<N> b = box;
+                        b[0][k] = run[0], b[1][k] = run[1];
+                        next.push_back(b);
+                    }
+                r.swap(next);
+            }
+            return r;
+        }
+
+        /// Intersection of every range of a list with one range
+        template <std::size_t N>
+        From_size<N> intersection(const From_size<N> &fs0, const Coor<N> &from1, const Coor<N> &size1,
+                                  const Coor<N> &dim) {
+            From_size<N> r;
+            for (const auto &it : fs0) {
+                From_size<N> p = intersection<N>(it[0], it[1], from1, size1, dim);
+                r.insert(r.end(), p.begin(), p.end());
+            }
+            return r;
+        }
+
+        /// Wall-clock time in seconds (reference: performance.h:228)
+        inline double w_time() {
+            return std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch())
+                .count();
+        }
+
+        inline int deviceId(const Cpu &) { return CPU_DEVICE_ID; }
+        inline int deviceId(const Gpu &g) { return g.device; }
+        inline void sync(const Cpu &) {}
+        inline void sync(const Gpu &g) { superbblas::sync(to_context(g)); }
+
+        /// Batched strided GEMM with the BLAS column-major convention (reference: blas.h:662 on GPUs,
+        /// blas_cpu_tmpl.hpp:376 on CPUs): c_i = alpha * op(a_i) * op(b_i) + beta * c_i.  Here it is
+        /// one launch of the fused contraction kernel: the transpositions are strides, 'c' is a flag.
+        template <typename T>
+        void xgemm_batch_strided(char transa, char transb, int m, int n, int k, T alpha, const T *a,
+                                 int lda, int stridea, const T *b, int ldb, int strideb, T beta, T *c,
+                                 int ldc, int stridec, int batch_size, Gpu xpu) {
+            if (m == 0 || n == 0 || batch_size == 0) return;
+            const bool ta = !(transa == 'n' || transa == 'N'), tb = !(transb == 'n' || transb == 'N');
+            sbk_contract_desc d;
+            std::memset(&d, 0, sizeof d);
+            d.nT = d.nM = d.nN = d.nK = 1;
+            d.T[0].size = batch_size, d.T[0].s0 = stridea, d.T[0].s1 = strideb, d.T[0].sr = stridec;
+            d.M[0].size = m, d.M[0].s0 = ta ? lda : 1, d.M[0].sr = 1;
+            d.N[0].size = n, d.N[0].s1 = tb ? 1 : ldb, d.N[0].sr = ldc;
+            d.K[0].size = k, d.K[0].s0 = ta ? 1 : lda, d.K[0].s1 = tb ? ldb : 1;
+            d.conj0 = transa == 'c' || transa == 'C', d.conj1 = transb == 'c' || transb == 'C';
+            const std::array<double, 2> al = scalar(alpha), be = scalar(beta);
+            check(sbk_contract(&d, dtype_of<T>::value, al.data(), (const void *)a, (const void *)b,
+                               be.data(), (void *)c, xpu.device, nullptr));
+        }
+
+        /// Host operands: staged through the GPU (there is no CPU compute path)
+        template <typename T>
+        void xgemm_batch_strided(char transa, char transb, int m, int n, int k, T alpha, const T *a,
+                                 int lda, int stridea, const T *b, int ldb, int strideb, T beta, T *c,
+                                 int ldc, int stridec, int batch_size, Cpu) {
+            if (m == 0 || n == 0 || batch_size == 0) return;
+            const bool ta = !(transa == 'n' || transa == 'N'), tb = !(transb == 'n' || transb == 'N');
+            auto extent = [&](int rows, int cols, int ld, int stride) {
+                return (std::size_t)(batch_size - 1) * stride + (std::size_t)(cols - 1) * ld + rows;
+            };
+            const std::size_t na = extent(ta ? k : m, ta ? m : k, lda, stridea),
+                              nb = extent(tb ? n : k, tb ? k : n, ldb, strideb),
+                              nc = extent(m, n, ldc, stridec);
+            Gpu gpu{0, 0};
+            Cpu cpu{};
+            vector<T, Gpu> da(na, gpu), db(nb, gpu), dc(nc, gpu);
+            copy_n<T>(a, cpu, na, da.data(), gpu);
+            copy_n<T>(b, cpu, nb, db.data(), gpu);
+            copy_n<T>(c, cpu, nc, dc.data(), gpu);
+            xgemm_batch_strided<T>(transa, transb, m, n, k, alpha, da.data(), lda, stridea, db.data(), ldb,
+                                   strideb, beta, dc.data(), ldc, stridec, batch_size, gpu);
+            copy_n<T>(dc.data(), gpu, nc, c, cpu);
+        }
     }
 
     // Diagnostics of the reference that callers and its tests reference; cheap no-ops here

@@ -45,6 +45,7 @@ namespace sbb {
             Group T, M, N, K;
             int conj0, conj1;
             int bn; // columns of an output tile of the mma kernel
+            int out_order[3]; // generic kernel: groups (0 = T, 1 = M, 2 = N) from fastest to slowest thread index
             int debug; // experiments only (SBB_MMA_DEBUG): 1 = no global loads in the main loop, 2 = also no barrier, 4 = no fragment loads
             // mma kernel
             int mtiles, ntiles, ksplit, ksteps; // ksteps = ceil(K/BK)
@@ -121,9 +122,24 @@ namespace sbb {
             const long long total = p.T.vol * p.M.vol * p.N.vol;
             for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
                  idx += (long long)gridDim.x * blockDim.x) {
-                // output enumeration: n fastest, then m, then t
-                const long long n = idx % p.N.vol, m = (idx / p.N.vol) % p.M.vol,
-                                t = idx / (p.N.vol * p.M.vol);
+                // output enumeration: n fastest, then m, then t -- or, opt-in (SBB_SIMT_ORDER=1), the
+                // group with the smallest output stride fastest, so that the stores are coalesced
+                long long n = idx % p.N.vol, m = (idx / p.N.vol) % p.M.vol,
+                          t = idx / (p.N.vol * p.M.vol);
+                if (p.out_order[0] != 2 || p.out_order[1] != 1) {
+                    long long rem = idx, g[3] = {0, 0, 0};
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const int grp = p.out_order[q];
+                        const long long vol = grp == 0 ? p.T.vol : grp == 1 ? p.M.vol : p.N.vol;
+                        const long long c = rem % vol;
+                        rem /= vol;
+                        if (grp == 0) g[0] = c;
+                        else if (grp == 1) g[1] = c;
+                        else g[2] = c;
+                    }
+                    t = g[0], m = g[1], n = g[2];
+                }
                 const long long o0 = group_offset(p.T, t, p.T.s0) + group_offset(p.M, m, p.M.s0);
                 const long long o1 = group_offset(p.T, t, p.T.s1) + group_offset(p.N, n, p.N.s1);
                 const long long orr = group_offset(p.T, t, p.T.sr) + group_offset(p.M, m, p.M.sr) +
@@ -701,7 +717,16 @@ namespace sbb {
         // An empty contracted range leaves vr = beta*vr: the generic kernel handles K.vol == 0
         const char *force = std::getenv("SBB_CONTRACT_KERNEL");
         const bool f64 = dtype == SBB_F64 || dtype == SBB_C128;
-        bool use_mma = p.K.vol >= 64 && p.M.vol * p.N.vol >= 256 && p.M.vol >= 8 && p.N.vol >= 8;
+        // The tensor-core kernel wants a real tile (M, N >= 8, M*N >= 256) -- or a long contraction
+        // with few outputs ("inner product" shapes, e.g. m = n = 1..12, k = 49152 of the reference's
+        // tests/dist.cpp): there the generic kernel has one thread per output and no parallelism
+        // over K, while the split-K of the tensor-core kernel fills the machine (the rows of the
+        // 64x64 tile beyond M, N are clamped re-reads of the last row: wasted DMMA work, but the
+        // operands are still read once).  The forced-"mma" parity tests cover tiny M and N.
+        const long long outputs = p.T.vol * p.M.vol * p.N.vol;
+        bool use_mma = p.K.vol >= 64 &&
+                       ((p.M.vol * p.N.vol >= 256 && p.M.vol >= 8 && p.N.vol >= 8) ||
+                        (p.K.vol >= 2048 && outputs < 148ll * 2048));
         if (force && std::strcmp(force, "simt") == 0) use_mma = false;
         if (force && std::strcmp(force, "mma") == 0 && p.K.vol > 0) use_mma = true;
         if (use_mma) {
@@ -761,6 +786,25 @@ namespace sbb {
             ss << "simt T=" << p.T.vol << " M=" << p.M.vol << " N=" << p.N.vol << " K=" << p.K.vol;
             *describe = ss.str();
             return;
+        }
+        p.out_order[0] = 2, p.out_order[1] = 1, p.out_order[2] = 0;
+        {
+            static int simt_order = -1;
+            if (simt_order < 0) {
+                const char *e = std::getenv("SBB_SIMT_ORDER");
+                simt_order = e ? std::atoi(e) : 0;
+            }
+            if (simt_order) {
+                auto min_sr = [](const Group &g) {
+                    long long s = 1ll << 62;
+                    for (int d = 0; d < g.n; ++d) s = std::min(s, g.sr[d] < 0 ? -g.sr[d] : g.sr[d]);
+                    return s;
+                };
+                const long long key[3] = {min_sr(p.T), min_sr(p.M), min_sr(p.N)};
+                int ord[3] = {2, 1, 0};
+                std::stable_sort(ord, ord + 3, [&](int a, int b) { return key[a] < key[b]; });
+                p.out_order[0] = ord[0], p.out_order[1] = ord[1], p.out_order[2] = ord[2];
+            }
         }
         switch (dtype) {
         case SBB_F32: launch_simt<float>(p, alpha, v0, v1, beta, vr, device, stream); break;

@@ -37,6 +37,21 @@ def test_reference_own_contraction_suite(nt, typ):
     _run_reference_suite(["--nt=%d" % nt, "--type=%s" % typ])
 
 
+def test_reference_own_dist_program():
+    """The reference's tests/dist.cpp, unchanged (tests/cxx/ref_dist_wrapper.cpp includes it from
+    /root/reference at build time), against include/superbblas.h: partition known answers and
+    make_hole checks (they throw on a wrong answer), then its permuting copies, shifts, halo fills,
+    detail::xgemm_batch_strided shapes and contractions with host and with GPU components.
+    Log of a run on a B200: profiles/r1_reference_dist_cpp_on_b200.log."""
+    exe = os.path.join(HERE, "cxx", "ref_dist_wrapper")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cxx/ref_dist_wrapper not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "--dim=16 16 16 32 16", "--reps=2"], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    assert ">>> GPU tests:" in r.stdout and "Time in copying halos out" in r.stdout
+
+
 # The wrapper also accepts --components=N (several components per process) and --cpu (host contexts,
 # staged through the GPU); they run the same enumeration but take much longer, so they are not part of
 # the default GPU test run.
