@@ -1,0 +1,114 @@
+// Host-only checks of the C++ drop-in front end (include/superbblas.h): everything here runs
+// without a GPU (partition generators, make_hole and the detail:: range helpers that the
+// reference's tests/dist.cpp uses), compared with brute-force enumeration of the lattice sites.
+// Built and run by tests/test_capi.py.
+#include "superbblas.h"
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <set>
+
+using namespace superbblas;
+using namespace superbblas::detail;
+
+#define CHECK(x)                                                                                   \
+    do {                                                                                           \
+        if (!(x)) {                                                                                \
+            std::printf("FAILED: %s (line %d)\n", #x, __LINE__);                                   \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+template <std::size_t N> static bool inside(const Coor<N> &c, const Coor<N> &from, const Coor<N> &size, const Coor<N> &dim) {
+    for (std::size_t k = 0; k < N; ++k)
+        if (((c[k] - from[k]) % dim[k] + dim[k]) % dim[k] >= size[k]) return false;
+    return true;
+}
+
+template <std::size_t N> static std::set<long> sites(const From_size<N> &fs, const Coor<N> &dim, bool &overlap) {
+    std::set<long> s;
+    overlap = false;
+    for (const auto &b : fs) {
+        std::size_t vol = volume<N>(b[1]);
+        for (std::size_t i = 0; i < vol; ++i) {
+            long idx = 0, stride = 1;
+            std::size_t r = i;
+            for (std::size_t k = 0; k < N; ++k) {
+                int c = (int)(r % b[1][k]);
+                r /= b[1][k];
+                idx += ((b[0][k] + c) % dim[k]) * stride;
+                stride *= dim[k];
+            }
+            if (!s.insert(idx).second) overlap = true;
+        }
+    }
+    return s;
+}
+
+int main() {
+    std::mt19937 rng(7);
+    auto rnd = [&](int lo, int hi) { return lo + (int)(rng() % (unsigned)(hi - lo + 1)); };
+    // detail::intersection against brute force, 3 dims, wrapping ranges included
+    for (int it = 0; it < 2000; ++it) {
+        Coor<3> dim{rnd(1, 6), rnd(1, 6), rnd(1, 6)}, f0, s0, f1, s1;
+        for (int k = 0; k < 3; ++k) {
+            f0[k] = rnd(0, dim[k] - 1), s0[k] = rnd(0, dim[k]);
+            f1[k] = rnd(0, dim[k] - 1), s1[k] = rnd(0, dim[k]);
+        }
+        From_size<3> r = intersection<3>(f0, s0, f1, s1, dim);
+        bool overlap;
+        std::set<long> got = sites<3>(r, dim, overlap);
+        CHECK(!overlap);
+        std::set<long> want;
+        for (int z = 0; z < dim[2]; ++z)
+            for (int y = 0; y < dim[1]; ++y)
+                for (int x = 0; x < dim[0]; ++x) {
+                    Coor<3> c{x, y, z};
+                    if (inside<3>(c, f0, s0, dim) && inside<3>(c, f1, s1, dim))
+                        want.insert(x + dim[0] * (y + dim[1] * z));
+                }
+        CHECK(got == want);
+        CHECK(volume<3>(r) == want.size());
+        // make_hole: the pieces are disjoint, inside (from,size), outside the hole, and cover the rest
+        auto h = make_hole<3>(f0, s0, f1, s1, dim);
+        std::set<long> hs = sites<3>(h, dim, overlap);
+        CHECK(!overlap);
+        std::set<long> hw;
+        for (int z = 0; z < dim[2]; ++z)
+            for (int y = 0; y < dim[1]; ++y)
+                for (int x = 0; x < dim[0]; ++x) {
+                    Coor<3> c{x, y, z};
+                    if (inside<3>(c, f0, s0, dim) && !inside<3>(c, f1, s1, dim))
+                        hw.insert(x + dim[0] * (y + dim[1] * z));
+                }
+        CHECK(hs == hw);
+    }
+    // known answers of the reference's tests/dist.cpp:103-125
+    {
+        Coor<5> dim{4, 4, 4, 4, 3};
+        CHECK((partitioning_distributed_procs<5>("xyztc", dim, "xyzt", 6) == Coor<5>{3, 2, 1, 1, 1}));
+        CHECK((partitioning_distributed_procs<5>("xyztc", dim, "xyzt", 7) == Coor<5>{3, 2, 1, 1, 1}));
+        Coor<5> dim1{4, 4, 4, 1, 3};
+        CHECK((partitioning_distributed_procs<5>("xyztc", dim1, "tzyx", 32) == Coor<5>{2, 4, 4, 1, 1}));
+    }
+    // basic_partitioning tiles the lattice exactly once
+    for (int it = 0; it < 200; ++it) {
+        Coor<3> dim{rnd(1, 7), rnd(1, 7), rnd(1, 7)}, procs{rnd(1, 3), rnd(1, 3), rnd(1, 2)};
+        auto p = basic_partitioning<3>("xyz", dim, procs, "zyx");
+        bool overlap;
+        std::set<long> s = sites<3>(p, dim, overlap);
+        CHECK(!overlap);
+        CHECK(s.size() == volume<3>(dim));
+    }
+    // error behaviour of the front end without touching a device
+    {
+        bool thrown = false;
+        try {
+            Coor<2> d{2, 2};
+            partitioning_distributed_procs<2>("x", d, "x", 2); // order too short
+        } catch (const std::runtime_error &) { thrown = true; }
+        CHECK(thrown);
+    }
+    std::printf("host api ok\n");
+    return 0;
+}

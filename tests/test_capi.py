@@ -88,3 +88,24 @@ def test_no_cuda_device_fails_loudly():
         assert "CUDA" in str(e) or "device" in str(e)
     else:
         raise AssertionError("copy must not succeed without a GPU (no CPU compute path)")
+
+
+def test_cxx_front_end_host_checks(tmp_path):
+    """include/superbblas.h compiled with plain g++ (no CUDA toolkit needed by callers): partition
+    generators, make_hole and the detail:: range helpers used by the reference's tests/dist.cpp,
+    against brute-force enumeration (tests/cxx/host_api_test.cpp).  Runs without a GPU."""
+    import shutil
+    import subprocess
+    import superbblas_b200
+    if not shutil.which("g++"):
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(superbblas_b200.LIB_PATH)
+    exe = str(tmp_path / "host_api_test")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"),
+                        os.path.join(root, "tests", "cxx", "host_api_test.cpp"), "-o", exe,
+                        "-L" + libdir, "-lsuperbblas_b200", "-Wl,-rpath," + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "host api ok" in r.stdout, r.stdout + r.stderr
