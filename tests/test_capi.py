@@ -5,6 +5,7 @@ import os
 import re
 
 import numpy as np
+import pytest
 
 import superbblas_b200 as sb
 from oracle import oracle as O
