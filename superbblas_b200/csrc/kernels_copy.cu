@@ -84,10 +84,6 @@ namespace sbb {
 
         // ---- element functors -----------------------------------------------------------------
 
-        template <typename T> struct is_cplx { static constexpr bool value = false; };
-        template <> struct is_cplx<float2> { static constexpr bool value = true; };
-        template <> struct is_cplx<double2> { static constexpr bool value = true; };
-
         __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
         __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
         __device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }

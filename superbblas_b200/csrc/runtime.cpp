@@ -720,19 +720,15 @@ namespace sbb {
         };
         if (use_p2p) {
             // ---- peer-memory exchange --------------------------------------------------------------
-            // pack kernels write into the receivers' arenas; one small all-reduce on the communication
-            // stream is the barrier "every rank's stores are done".  The arena halves alternate, and
-            // every call ends with the compute stream waiting for the barrier, so a sender can only
-            // overwrite a half after its previous readers have finished.
+            // pack kernels write into the receivers' arenas and raise this rank's flag there when their
+            // last CTA is done (or, SBB_P2P_SIGNAL=0, one small all-reduce on the communication stream
+            // is the barrier "every rank's stores are done").  The arena halves alternate, and every
+            // call ends with the compute stream waiting for every rank's last signal, so a sender can
+            // only overwrite a half after its previous readers have finished.
             // The exchange is cut in rounds (windows of `chunk` bytes of every segment): round k's
             // unpack kernels (auxiliary stream) overlap the pack kernels of the later rounds
             // (compute stream); the pack kernels run on a reduced grid because NVLink, not HBM,
             // bounds them, which leaves SM resources for the kernels on the auxiliary stream.
-            const int64_t chunk = std::max<int64_t>(args.chunk_bytes, 1);
-            auto round_of = [&](const BoxOp &op) {
-                const int64_t off = (op.kind == BoxOp::Pack ? op.doff : op.soff) * esw;
-                return args.chunk_bytes > 0 ? (int)(off / chunk) : 0;
-            };
             // all ranks run the same number of barriers: the round count comes from the largest
             // message of the whole exchange
             const int nrounds = args.chunk_bytes > 0
@@ -954,7 +950,6 @@ namespace sbb {
                     for (const auto &op : plan.ops)
                         if (op.kind == BoxOp::Unpack && round_of(op) == k) run(op);
                 }
-                if (nrounds == 0) (void)0;
             }
             set_grid_cap(0);
         } else {
