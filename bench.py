@@ -126,6 +126,29 @@ def run_reference(args):
     return 0
 
 
+def bind_host_to_gpu_numa(torch, local):
+    """N > 1: keep this rank's host threads -- and therefore its pinned staging buffers (first touch)
+    -- on the CPUs NVML names as local to its GPU, so that the host->device copies of the e2e leg do
+    not cross sockets.  Best effort: returns the number of CPUs bound to, or None when anything is
+    missing (SBB_BENCH_NUMA=0 disables it).  Not used at N = 1, where the CPU baseline needs every core."""
+    if os.environ.get("SBB_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        u = str(torch.cuda.get_device_properties(local).uuid)
+        if not u.startswith("GPU-"):
+            u = "GPU-" + u
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(u)
+        except TypeError:
+            h = pynvml.nvmlDeviceGetHandleByUUID(u.encode())
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def workload_config(n):
     pz, pt = grid_for(n)
     return {"workload": "BASELINE configs[1] per GPU: contraction cxyztn^H . cxyztm -> tnm, "
@@ -218,6 +241,7 @@ def main():
             raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_affinity = bind_host_to_gpu_numa(torch, local) if world > 1 else None
     comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -419,6 +443,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "ms_per_step": ms_e2e / e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "result_check": check_ok,
+            "host_cpus_bound_to_gpu_numa": host_affinity,
             "reshuffle": extras, "contraction_c64": contraction_c64, "hbm_peak_gbs": hbm_peak,
             "hbm_peak_source": hbm_src,
         }
