@@ -110,3 +110,20 @@ def test_cxx_front_end_host_checks(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "host api ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("program", ["dist.cpp", "contract.cpp"])
+def test_reference_tests_compile_against_the_drop_in_header(program):
+    """The reference's own test programs, unchanged, are valid callers of include/superbblas.h --
+    also in their MPI configuration (SUPERBBLAS_USE_MPI, compile-checked against the stand-in
+    tests/cxx/mpi_stub/mpi.h).  Syntax and template instantiation only; the GPU tests run them."""
+    import shutil
+    import subprocess
+    src = os.path.join("/root/reference/tests", program)
+    if not os.path.exists(src) or not shutil.which("g++"):
+        pytest.skip("needs /root/reference and g++")
+    for defs in (["-DSUPERBBLAS_USE_GPU"], ["-DSUPERBBLAS_USE_GPU", "-DSUPERBBLAS_USE_MPI"]):
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w"] + defs +
+                           ["-I" + os.path.join(ROOT, "tests", "cxx", "mpi_stub"),
+                            "-I" + os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+        assert r.returncode == 0, (defs, r.stderr[-2000:])
