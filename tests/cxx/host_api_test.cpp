@@ -109,6 +109,35 @@ int main() {
         } catch (const std::runtime_error &) { thrown = true; }
         CHECK(thrown);
     }
+    // local_copy / local_contraction (signatures of the reference's tests/local.cpp): without a CUDA
+    // device they must fail loudly (there is no CPU compute path); with one, give the right answer
+    {
+        Coor<2> d{2, 3}, dt{3, 2};
+        std::vector<double> x{1, 2, 3, 4, 5, 6}, y(6, -1.0), z(4, -1.0);
+        Context cpu = createCpuContext();
+        bool thrown = false;
+        try {
+            local_copy<2, 2, double, double>(2.0, "xy", Coor<2>{}, d, d, x.data(), nullptr, cpu, "yx",
+                                             Coor<2>{}, dt, y.data(), nullptr, cpu, FastToSlow, Copy);
+            Coor<2> dr{2, 2};
+            local_contraction<2, 2, 2, double>(1.0, "xy", d, false, x.data(), "zy", d, false, x.data(),
+                                               0.0, "xz", dr, z.data(), cpu, FastToSlow);
+        } catch (const std::runtime_error &e) {
+            thrown = true;
+            std::printf("no device: %s\n", e.what());
+        }
+        if (!thrown) {
+            // y[j + 3 i] = 2 x[i + 2 j];  z[i + 2 k] = sum_j x[i + 2 j] x[k + 2 j]
+            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 3; ++j) CHECK(y[j + 3 * i] == 2 * x[i + 2 * j]);
+            for (int i = 0; i < 2; ++i)
+                for (int k = 0; k < 2; ++k) {
+                    double acc = 0;
+                    for (int j = 0; j < 3; ++j) acc += x[i + 2 * j] * x[k + 2 * j];
+                    CHECK(z[i + 2 * k] == acc);
+                }
+        }
+    }
     std::printf("host api ok\n");
     return 0;
 }

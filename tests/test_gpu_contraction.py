@@ -138,6 +138,26 @@ def test_large_contraction_properties(gu):
     assert rel < 1e-12, rel
 
 
+def test_local_contraction_wrapper(gu):
+    """local_contraction (signature of the reference's tests/local.cpp:163) against the oracle."""
+    import torch
+    gpu = sb.createGpuContext(0)
+    for dtype, tol in ((np.complex128, 1e-12), (np.float32, 1e-5)):
+        dim0, dim1, dimr = [5, 7, 3], [7, 4, 3], [3, 5, 4]  # "akt" . "kbt" -> "tab"
+        case = dict(alpha=1, beta=0, p0=_single(dim0), from0=[0] * 3, size0=dim0, dim0=dim0, o0="akt",
+                    conj0=True, p1=_single(dim1), from1=[0] * 3, size1=dim1, dim1=dim1, o1="kbt",
+                    conj1=False, pr=_single(dimr), fromr=[0] * 3, sizer=dimr, dimr=dimr, o_r="tab",
+                    co=1, T=np.dtype(dtype))
+        v0, v1, vr = C.make_contraction_data(case, 9)
+        want = C.oracle_contraction(case, v0, v1, vr)
+        d0, d1, dr = (torch.from_numpy(x[0]).cuda() for x in (v0, v1, vr))
+        sb.local_contraction(1, "akt", dim0, True, d0, "kbt", dim1, False, d1, 0, "tab", dimr, dr, gpu,
+                             sb.FastToSlow)
+        sb.sync(gpu)
+        ok, err = close([dr.cpu().numpy()], want, tol)
+        assert ok, (dtype, err)
+
+
 def test_contraction_errors(gu):
     import torch
     gpu = sb.createGpuContext(0)

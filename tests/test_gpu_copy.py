@@ -249,6 +249,29 @@ def test_golden_vectors_on_gpu(gu):
             assert C.bits_equal(x, w), (name, j)
 
 
+def test_local_copy_wrapper(gu):
+    """local_copy (north-star API; signature of the reference's tests/local.cpp:97): one component on
+    each side, with and without masks, against the oracle's copy with a single PartitionItem."""
+    import torch
+    rng = np.random.default_rng(1700)
+    gpu = sb.createGpuContext(0)
+    for it in range(30):
+        case = C.random_copy_case(rng, nparts0=1, nparts1=1, max_dim=6)
+        case["p0"] = np.array([[[0] * len(case["dim0"]), case["dim0"]]], dtype=np.int32)
+        case["p1"] = np.array([[[0] * len(case["dim1"]), case["dim1"]]], dtype=np.int32)
+        v0, v1 = C.make_copy_data(case, 800 + it, consistent=True)
+        m0, m1 = C.make_masks(case, 800 + it) if it % 2 else (None, None)
+        want = C.oracle_copy(case, v0, v1, m0, m1)
+        a, b = torch.from_numpy(v0[0]).cuda(), torch.from_numpy(v1[0]).cuda()
+        dm0 = torch.from_numpy(m0[0]).cuda() if m0 is not None else None
+        dm1 = torch.from_numpy(m1[0]).cuda() if m1 is not None else None
+        sb.local_copy(case["alpha"], case["o0"], case["from0"], case["size0"], case["dim0"], a, dm0,
+                      gpu, case["o1"], case["from1"], case["dim1"], b, dm1, gpu, case["co"],
+                      case["copyadd"])
+        sb.sync(gpu)
+        assert C.bits_equal(b.cpu().numpy(), want[0]), (it, case)
+
+
 def test_errors(gu):
     import torch
     gpu = sb.createGpuContext(0)
