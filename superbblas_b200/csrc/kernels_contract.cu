@@ -20,6 +20,7 @@
 //  * contract_simt_kernel: any type, any shape; one thread per output element, K loop in registers,
 //    float types accumulate in double.  Used for small problems (e.g. site-wise colour-spin
 //    contractions with M=N=1) and for float / complex float.
+#include "contract_row.hpp"
 #include "kernels.hpp"
 #include "runtime.hpp"
 #include <algorithm>
@@ -166,6 +167,18 @@ namespace sbb {
                 if (!is_zero_acc(beta)) r = addc(r, mulc(beta, widen(vr[orr])));
                 vr[orr] = narrow<T>(r);
             }
+        }
+
+        // ---- row kernel (short contraction, one small free group; body in contract_row.hpp) ----------
+
+        template <typename T>
+        __global__ void __launch_bounds__(128)
+            contract_row_kernel(const __grid_constant__ rowk::RowParams p, const T *__restrict__ va,
+                                const T *__restrict__ vb, T *vr, typename rowk::Acc<T>::type alpha,
+                                typename rowk::Acc<T>::type beta) {
+            for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < p.rows;
+                 row += (long long)gridDim.x * blockDim.x)
+                rowk::row_body<T>(p, row, va, vb, vr, alpha, beta);
         }
 
         // ---- FP64 tensor-core kernel -----------------------------------------------------------------
@@ -594,6 +607,19 @@ namespace sbb {
         template <> double2 scalar_of<double2>(const double *a) { return make_double2(a[0], a[1]); }
 
         template <typename T>
+        void launch_row(const rowk::RowParams &rp, bool swapped, const double *alpha, const void *v0,
+                        const void *v1, const double *beta, void *vr, int device, cudaStream_t stream) {
+            using A = typename Acc<T>::type;
+            const unsigned grid =
+                (unsigned)std::min<long long>((rp.rows + 127) / 128, (long long)sm_count(device) * 12);
+            contract_row_kernel<T><<<grid, 128, 0, stream>>>(rp, (const T *)(swapped ? v1 : v0),
+                                                            (const T *)(swapped ? v0 : v1), (T *)vr,
+                                                            scalar_of<A>(alpha), scalar_of<A>(beta));
+            count_launch();
+            cuda_check(cudaGetLastError(), "contract_row_kernel launch");
+        }
+
+        template <typename T>
         void launch_simt(const ContractParams &p, const double *alpha, const void *v0, const void *v1,
                          const double *beta, void *vr, int device, cudaStream_t stream) {
             using A = typename Acc<T>::type;
@@ -729,6 +755,32 @@ namespace sbb {
                         (p.K.vol >= 2048 && outputs < 148ll * 2048));
         if (force && std::strcmp(force, "simt") == 0) use_mma = false;
         if (force && std::strcmp(force, "mma") == 0 && p.K.vol > 0) use_mma = true;
+        // Opt-in (SBB_ROW_KERNEL=1, not yet validated on a B200; its body is checked on the CPU by
+        // tests/test_row_kernel_emulation.py): short contractions with one small free group
+        static int row_env = -1;
+        if (row_env < 0) {
+            const char *e = std::getenv("SBB_ROW_KERNEL");
+            row_env = e ? std::atoi(e) : 0;
+        }
+        if (row_env && !force && !use_mma && rowk::eligible(desc)) {
+            rowk::RowParams rp;
+            bool swapped = false;
+            rowk::build(desc, rp, swapped);
+            if (describe) {
+                std::stringstream ss;
+                ss << "row rows=" << rp.rows << " small=" << rp.ns << " K=" << rp.nk
+                   << " big_operand=" << (swapped ? "v1" : "v0");
+                *describe = ss.str();
+                return;
+            }
+            switch (dtype) {
+            case SBB_F32: launch_row<float>(rp, swapped, alpha, v0, v1, beta, vr, device, stream); break;
+            case SBB_F64: launch_row<double>(rp, swapped, alpha, v0, v1, beta, vr, device, stream); break;
+            case SBB_C64: launch_row<float2>(rp, swapped, alpha, v0, v1, beta, vr, device, stream); break;
+            case SBB_C128: launch_row<double2>(rp, swapped, alpha, v0, v1, beta, vr, device, stream); break;
+            }
+            return;
+        }
         if (use_mma) {
             // tile shape: 64x64 (2 CTAs/SM) or 64x32 (3 CTAs/SM, more warps to hide latencies);
             // SBB_MMA_BN overrides for experiments

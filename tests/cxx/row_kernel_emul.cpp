@@ -1,0 +1,39 @@
+// TEST INFRASTRUCTURE: runs the body of the contraction row kernel (superbblas_b200/csrc/contract_row.hpp,
+// the same host/device function the CUDA kernel calls) one row at a time on the CPU, so that its indexing
+// and arithmetic are checked without a GPU (tests/test_row_kernel_emulation.py).  Not part of the product.
+#include "../../superbblas_b200/csrc/contract_row.hpp"
+
+using namespace sbb::rowk;
+
+template <typename T> static typename Acc<T>::type scalar(const double *a);
+template <> double scalar<float>(const double *a) { return a[0]; }
+template <> double scalar<double>(const double *a) { return a[0]; }
+template <> double2 scalar<float2>(const double *a) { double2 r; r.x = a[0], r.y = a[1]; return r; }
+template <> double2 scalar<double2>(const double *a) { double2 r; r.x = a[0], r.y = a[1]; return r; }
+
+template <typename T>
+static void run(const RowParams &p, bool swapped, const double *alpha, const void *v0, const void *v1,
+                const double *beta, void *vr) {
+    const T *va = (const T *)(swapped ? v1 : v0), *vb = (const T *)(swapped ? v0 : v1);
+    for (long long row = 0; row < p.rows; ++row)
+        row_body<T>(p, row, va, vb, (T *)vr, scalar<T>(alpha), scalar<T>(beta));
+}
+
+extern "C" int rowk_eligible(const sbk_contract_desc *desc) { return eligible(*desc) ? 1 : 0; }
+
+extern "C" int rowk_emulate(const sbk_contract_desc *desc, int dtype, const double *alpha, const void *v0,
+                            const void *v1, const double *beta, void *vr) {
+    try {
+        RowParams p;
+        bool swapped = false;
+        build(*desc, p, swapped);
+        switch (dtype) {
+        case SBB_F32: run<float>(p, swapped, alpha, v0, v1, beta, vr); break;
+        case SBB_F64: run<double>(p, swapped, alpha, v0, v1, beta, vr); break;
+        case SBB_C64: run<float2>(p, swapped, alpha, v0, v1, beta, vr); break;
+        case SBB_C128: run<double2>(p, swapped, alpha, v0, v1, beta, vr); break;
+        default: return 2;
+        }
+        return 0;
+    } catch (const std::exception &) { return 1; }
+}
