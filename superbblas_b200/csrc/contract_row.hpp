@@ -124,6 +124,35 @@ namespace sbb {
                 }
         }
 
+        // ---- output enumeration of the generic kernel (opt-in SBB_SIMT_ORDER=1) --------------------------
+        /// Thread index -> (t, m, n) with the groups listed in `order` (0 = T, 1 = M, 2 = N) from the
+        /// fastest to the slowest; {2, 1, 0} is the kernel's default (n fastest, then m, then t)
+        SBB_HD void output_index(const int *order, long long tvol, long long mvol, long long nvol,
+                                 long long idx, long long &t, long long &m, long long &n) {
+            long long g[3] = {0, 0, 0};
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int grp = order[q];
+                const long long vol = grp == 0 ? tvol : grp == 1 ? mvol : nvol;
+                const long long c = idx % vol;
+                idx /= vol;
+                if (grp == 0) g[0] = c;
+                else if (grp == 1) g[1] = c;
+                else g[2] = c;
+            }
+            t = g[0], m = g[1], n = g[2];
+        }
+
+        /// Groups ordered by their smallest result stride (ties and absent groups keep {N, M, T})
+        inline void output_order(const long long min_sr[3], int *order) {
+            order[0] = 2, order[1] = 1, order[2] = 0;
+            for (int i = 1; i < 3; ++i)
+                for (int j = i; j > 0 && min_sr[order[j]] < min_sr[order[j - 1]]; --j) {
+                    const int x = order[j];
+                    order[j] = order[j - 1], order[j - 1] = x;
+                }
+        }
+
         // ---- host: parameters from a contraction descriptor -------------------------------------------
 
         struct Dim {

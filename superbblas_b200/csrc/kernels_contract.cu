@@ -127,20 +127,8 @@ namespace sbb {
                 // group with the smallest output stride fastest, so that the stores are coalesced
                 long long n = idx % p.N.vol, m = (idx / p.N.vol) % p.M.vol,
                           t = idx / (p.N.vol * p.M.vol);
-                if (p.out_order[0] != 2 || p.out_order[1] != 1) {
-                    long long rem = idx, g[3] = {0, 0, 0};
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const int grp = p.out_order[q];
-                        const long long vol = grp == 0 ? p.T.vol : grp == 1 ? p.M.vol : p.N.vol;
-                        const long long c = rem % vol;
-                        rem /= vol;
-                        if (grp == 0) g[0] = c;
-                        else if (grp == 1) g[1] = c;
-                        else g[2] = c;
-                    }
-                    t = g[0], m = g[1], n = g[2];
-                }
+                if (p.out_order[0] != 2 || p.out_order[1] != 1)
+                    rowk::output_index(p.out_order, p.T.vol, p.M.vol, p.N.vol, idx, t, m, n);
                 const long long o0 = group_offset(p.T, t, p.T.s0) + group_offset(p.M, m, p.M.s0);
                 const long long o1 = group_offset(p.T, t, p.T.s1) + group_offset(p.N, n, p.N.s1);
                 const long long orr = group_offset(p.T, t, p.T.sr) + group_offset(p.M, m, p.M.sr) +
@@ -853,9 +841,7 @@ namespace sbb {
                     return s;
                 };
                 const long long key[3] = {min_sr(p.T), min_sr(p.M), min_sr(p.N)};
-                int ord[3] = {2, 1, 0};
-                std::stable_sort(ord, ord + 3, [&](int a, int b) { return key[a] < key[b]; });
-                p.out_order[0] = ord[0], p.out_order[1] = ord[1], p.out_order[2] = ord[2];
+                rowk::output_order(key, p.out_order);
             }
         }
         switch (dtype) {

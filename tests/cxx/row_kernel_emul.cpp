@@ -37,3 +37,10 @@ extern "C" int rowk_emulate(const sbk_contract_desc *desc, int dtype, const doub
         return 0;
     } catch (const std::exception &) { return 1; }
 }
+
+// generic kernel's opt-in output enumeration: (order chosen from the strides, then idx -> t, m, n)
+extern "C" void rowk_output_order(const long long *min_sr, int *order) { output_order(min_sr, order); }
+extern "C" void rowk_output_index(const int *order, long long tvol, long long mvol, long long nvol,
+                                  long long idx, long long *tmn) {
+    output_index(order, tvol, mvol, nvol, idx, tmn[0], tmn[1], tmn[2]);
+}

@@ -119,3 +119,31 @@ def test_row_kernel_body_against_numpy(emul, dtype):
         assert err < tol, (it, err)
         ran += 1
     assert ran >= 150
+
+
+def test_output_enumeration_is_a_bijection_along_the_smallest_stride(emul):
+    """SBB_SIMT_ORDER=1: every output is visited exactly once and consecutive threads walk the group
+    with the smallest result stride."""
+    rng = np.random.default_rng(2200)
+    emul.rowk_output_index.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_longlong, ctypes.c_longlong,
+                                       ctypes.c_longlong, ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong)]
+    for it in range(200):
+        vol = [int(rng.integers(1, 6)) for _ in range(3)]  # T, M, N
+        key = [int(x) for x in rng.permutation([1, 7, 50])] if it % 4 else [5, 5, 5]
+        min_sr = (ctypes.c_longlong * 3)(*key)
+        order = (ctypes.c_int * 3)()
+        emul.rowk_output_order(min_sr, order)
+        assert sorted(order) == [0, 1, 2]
+        assert [key[g] for g in order] == sorted(key)
+        if it % 4 == 0:
+            assert list(order) == [2, 1, 0]  # ties keep the default enumeration
+        seen = set()
+        tmn = (ctypes.c_longlong * 3)()
+        for idx in range(vol[0] * vol[1] * vol[2]):
+            emul.rowk_output_index(order, vol[0], vol[1], vol[2], idx, tmn)
+            c = tuple(tmn)
+            assert all(0 <= c[g] < vol[g] for g in range(3))
+            seen.add(c)
+            if idx == 1 and vol[order[0]] > 1:
+                assert c[order[0]] == 1  # the fastest group advances first
+        assert len(seen) == vol[0] * vol[1] * vol[2]
