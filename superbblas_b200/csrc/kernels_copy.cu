@@ -446,11 +446,14 @@ namespace sbb {
                 if (tid == 0) {
                     const unsigned prev = atomicAdd(xs.done, 1u);
                     if (prev + 1 == gridDim.x) {
+                        // one system-scope fence orders every CTA's stores (each fenced before its
+                        // atomicAdd) before the flag stores, which can then be relaxed and pipelined
+                        // (a release store per peer would pay the fence once per peer)
                         __threadfence_system();
                         atomicExch(xs.done, 0u); // the next user is ordered behind this kernel
                         for (int q = 0; q < xs.nranks; ++q) {
                             unsigned long long *f = xs.peer_flags[q] + xs.me;
-                            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(xs.sig_seq)
+                            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(xs.sig_seq)
                                          : "memory");
                         }
                     }
