@@ -20,6 +20,7 @@
 //  * contract_simt_kernel: any type, any shape; one thread per output element, K loop in registers,
 //    float types accumulate in double.  Used for small problems (e.g. site-wise colour-spin
 //    contractions with M=N=1) and for float / complex float.
+#include "contract_dot.hpp"
 #include "contract_row.hpp"
 #include "kernels.hpp"
 #include "runtime.hpp"
@@ -167,6 +168,29 @@ namespace sbb {
             for (long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x; row < p.rows;
                  row += (long long)gridDim.x * blockDim.x)
                 rowk::row_body<T>(p, row, va, vb, vr, alpha, beta);
+        }
+
+        // ---- dot kernel (long contraction, both free groups small; bodies in contract_dot.hpp) -------
+
+        template <typename T>
+        __global__ void __launch_bounds__(128)
+            contract_dot_partial_kernel(const __grid_constant__ dotk::DotParams p,
+                                        const T *__restrict__ va, const T *__restrict__ vb,
+                                        typename rowk::Acc<T>::type *__restrict__ ws) {
+            const long long thread = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+            if (thread < dotk::threads_of(p)) dotk::dot_partial<T>(p, thread, va, vb, ws);
+        }
+
+        template <typename T>
+        __global__ void __launch_bounds__(256)
+            contract_dot_reduce_kernel(const __grid_constant__ dotk::DotParams p,
+                                       const typename rowk::Acc<T>::type *__restrict__ ws, T *vr,
+                                       typename rowk::Acc<T>::type alpha,
+                                       typename rowk::Acc<T>::type beta) {
+            const long long total = dotk::outputs_of(p);
+            for (long long out = blockIdx.x * (long long)blockDim.x + threadIdx.x; out < total;
+                 out += (long long)gridDim.x * blockDim.x)
+                dotk::dot_reduce<T>(p, out, ws, vr, alpha, beta);
         }
 
         // ---- FP64 tensor-core kernel -----------------------------------------------------------------
@@ -608,6 +632,26 @@ namespace sbb {
         }
 
         template <typename T>
+        void launch_dot(const dotk::DotParams &dp, const double *alpha, const void *v0, const void *v1,
+                        const double *beta, void *vr, int device, cudaStream_t stream) {
+            using A = typename Acc<T>::type;
+            const long long threads = dotk::threads_of(dp);
+            A *ws = (A *)pool_alloc(device, (size_t)threads * dotk::SB * dotk::SB * sizeof(A));
+            contract_dot_partial_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(
+                dp, (const T *)v0, (const T *)v1, ws);
+            count_launch();
+            cuda_check(cudaGetLastError(), "contract_dot_partial_kernel launch");
+            const long long outs = dotk::outputs_of(dp);
+            const unsigned grid =
+                (unsigned)std::min<long long>((outs + 255) / 256, (long long)sm_count(device) * 8);
+            contract_dot_reduce_kernel<T><<<grid, 256, 0, stream>>>(dp, ws, (T *)vr, scalar_of<A>(alpha),
+                                                                  scalar_of<A>(beta));
+            count_launch();
+            cuda_check(cudaGetLastError(), "contract_dot_reduce_kernel launch");
+            pool_free(device, ws);
+        }
+
+        template <typename T>
         void launch_simt(const ContractParams &p, const double *alpha, const void *v0, const void *v1,
                          const double *beta, void *vr, int device, cudaStream_t stream) {
             using A = typename Acc<T>::type;
@@ -749,6 +793,33 @@ namespace sbb {
         if (row_env < 0) {
             const char *e = std::getenv("SBB_ROW_KERNEL");
             row_env = e ? std::atoi(e) : 0;
+        }
+        // Opt-in (SBB_DOT_KERNEL=1, same status; bodies checked on the CPU): long contractions whose
+        // free groups are both small
+        static int dot_env = -1;
+        if (dot_env < 0) {
+            const char *e = std::getenv("SBB_DOT_KERNEL");
+            dot_env = e ? std::atoi(e) : 0;
+        }
+        if (dot_env && !force && p.K.vol >= 1024 && dotk::eligible(desc)) {
+            dotk::DotParams dp;
+            dotk::build(desc, dp, (long long)sm_count(device) * 2048);
+            if (dotk::threads_of(dp) <= (1ll << 22)) {
+                if (describe) {
+                    std::stringstream ss;
+                    ss << "dot T=" << dp.tvol << " M=" << dp.m << " N=" << dp.n << " K=" << dp.kvol
+                       << " slices=" << dp.slices << " blocks=" << dp.pgm << "x" << dp.pgn;
+                    *describe = ss.str();
+                    return;
+                }
+                switch (dtype) {
+                case SBB_F32: launch_dot<float>(dp, alpha, v0, v1, beta, vr, device, stream); break;
+                case SBB_F64: launch_dot<double>(dp, alpha, v0, v1, beta, vr, device, stream); break;
+                case SBB_C64: launch_dot<float2>(dp, alpha, v0, v1, beta, vr, device, stream); break;
+                case SBB_C128: launch_dot<double2>(dp, alpha, v0, v1, beta, vr, device, stream); break;
+                }
+                return;
+            }
         }
         if (row_env && !force && !use_mma && rowk::eligible(desc)) {
             rowk::RowParams rp;

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE: runs the body of the contraction row kernel (superbblas_b200/csrc/contract_row.hpp,
 // the same host/device function the CUDA kernel calls) one row at a time on the CPU, so that its indexing
 // and arithmetic are checked without a GPU (tests/test_row_kernel_emulation.py).  Not part of the product.
-#include "../../superbblas_b200/csrc/contract_row.hpp"
+#include "../../superbblas_b200/csrc/contract_dot.hpp"
 
 using namespace sbb::rowk;
 
@@ -43,4 +43,35 @@ extern "C" void rowk_output_order(const long long *min_sr, int *order) { output_
 extern "C" void rowk_output_index(const int *order, long long tvol, long long mvol, long long nvol,
                                   long long idx, long long *tmn) {
     output_index(order, tvol, mvol, nvol, idx, tmn[0], tmn[1], tmn[2]);
+}
+
+// ---- dot kernel (long contraction, both free groups small): both passes, thread by thread -----------------
+template <typename T>
+static void run_dot(const sbb::dotk::DotParams &p, const double *alpha, const void *v0, const void *v1,
+                    const double *beta, void *vr) {
+    using A = typename Acc<T>::type;
+    std::vector<A> ws((size_t)sbb::dotk::threads_of(p) * sbb::dotk::SB * sbb::dotk::SB);
+    for (long long th = 0; th < sbb::dotk::threads_of(p); ++th)
+        sbb::dotk::dot_partial<T>(p, th, (const T *)v0, (const T *)v1, ws.data());
+    for (long long o = 0; o < sbb::dotk::outputs_of(p); ++o)
+        sbb::dotk::dot_reduce<T>(p, o, ws.data(), (T *)vr, scalar<T>(alpha), scalar<T>(beta));
+}
+
+extern "C" int dotk_eligible(const sbk_contract_desc *desc) { return sbb::dotk::eligible(*desc) ? 1 : 0; }
+
+extern "C" int dotk_emulate(const sbk_contract_desc *desc, int dtype, long long target_threads,
+                            const double *alpha, const void *v0, const void *v1, const double *beta,
+                            void *vr) {
+    try {
+        sbb::dotk::DotParams p;
+        sbb::dotk::build(*desc, p, target_threads);
+        switch (dtype) {
+        case SBB_F32: run_dot<float>(p, alpha, v0, v1, beta, vr); break;
+        case SBB_F64: run_dot<double>(p, alpha, v0, v1, beta, vr); break;
+        case SBB_C64: run_dot<float2>(p, alpha, v0, v1, beta, vr); break;
+        case SBB_C128: run_dot<double2>(p, alpha, v0, v1, beta, vr); break;
+        default: return 2;
+        }
+        return 0;
+    } catch (const std::exception &) { return 1; }
 }

@@ -41,15 +41,19 @@ def emul(tmp_path_factory):
     return ctypes.CDLL(so)
 
 
-def _problem(rng, dtype):
-    """Random contraction with one big and one small free group; every tensor stored in its own
-    random label order (so all strides are exercised)."""
+def _problem(rng, dtype, long_k=False):
+    """Random contraction with one big and one small free group (or, long_k, two small free groups
+    and a long contraction); every tensor stored in its own random label order (so all strides are
+    exercised)."""
     groups = {g: [(g + str(i), int(rng.integers(1, 5))) for i in range(int(rng.integers(0, 3)))]
               for g in "TMNK"}
     if not groups["K"]:
         groups["K"] = [("K0", int(rng.integers(1, 5)))]
-    big = "M" if rng.random() < 0.5 else "N"
-    groups[big].append((big + "x", int(rng.integers(5, 40))))  # make one free group the big one
+    if long_k:
+        groups["K"].append(("Kx", int(rng.integers(20, 200))))
+    else:
+        big = "M" if rng.random() < 0.5 else "N"
+        groups[big].append((big + "x", int(rng.integers(5, 40))))  # make one free group the big one
     size = {name: s for g in groups.values() for name, s in g}
 
     def tensor(labels):
@@ -147,3 +151,37 @@ def test_output_enumeration_is_a_bijection_along_the_smallest_stride(emul):
             if idx == 1 and vol[order[0]] > 1:
                 assert c[order[0]] == 1  # the fastest group advances first
         assert len(seen) == vol[0] * vol[1] * vol[2]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.complex64, np.complex128])
+def test_dot_kernel_passes_against_numpy(emul, dtype):
+    """contract_dot.hpp: partial sums per k slice and 4x4 block (pass 1), ordered reduction with
+    alpha/beta (pass 2), for several slice counts."""
+    rng = np.random.default_rng(2300 + np.dtype(dtype).itemsize + (np.dtype(dtype).kind == "c"))
+    DT = {np.float32: sb.F32, np.float64: sb.F64, np.complex64: sb.C64, np.complex128: sb.C128}[dtype]
+    cplx = np.dtype(dtype).kind == "c"
+    tol = 1e-5 if np.dtype(dtype).itemsize // (2 if cplx else 1) == 4 else 1e-12
+    emul.dotk_emulate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    ran = 0
+    for it in range(200):
+        desc, v0, v1, vr, ref = _problem(rng, dtype, long_k=True)
+        if not emul.dotk_eligible(ctypes.byref(desc)):
+            continue
+        alpha = [1, -1, 0.5 - (1.5j if cplx else 0)][it % 3]
+        beta = [0, 1, -0.25 + (0.5j if cplx else 0)][(it // 3) % 3]
+        want = alpha * ref + beta * vr.astype(np.complex128)
+        if beta == 0:
+            vr[:] = np.nan
+        out = vr.copy()
+        a, b = api._scalar(alpha), api._scalar(beta)
+        rc = emul.dotk_emulate(ctypes.addressof(desc), DT, [64, 1000, 100000][it % 3],
+                               ctypes.addressof(a), v0.ctypes.data, v1.ctypes.data, ctypes.addressof(b),
+                               out.ctypes.data)
+        assert rc == 0
+        if not cplx:
+            want = want.real
+        err = np.linalg.norm(out.astype(np.complex128) - want) / max(np.linalg.norm(want), 1e-30)
+        assert err < tol, (it, err)
+        ran += 1
+    assert ran >= 100
