@@ -138,6 +138,39 @@ def test_large_contraction_properties(gu):
     assert rel < 1e-12, rel
 
 
+@pytest.mark.parametrize("dtype", [np.complex128, np.complex64])
+def test_skinny_shapes_of_the_reference_dist_program(gu, dtype):
+    """The batched-GEMM shapes the reference's tests/dist.cpp times (there without checking them):
+    "inner product" (m = n small, k long) and "update" (m long, n = k small), here against a torch
+    einsum in complex128.  Whatever kernel the dispatcher picks (tensor-core split-K, generic, or the
+    opt-in row / dot kernels) must agree."""
+    import torch
+    gpu = sb.createGpuContext(0)
+    tdt = torch.complex128 if dtype == np.complex128 else torch.complex64
+    tol = TOL[np.dtype(dtype)]
+    g = torch.Generator(device="cuda").manual_seed(17)
+
+    def rnd(n):
+        real = torch.float64 if tdt == torch.complex128 else torch.float32
+        return torch.view_as_complex(torch.rand(n, 2, generator=g, device="cuda", dtype=real) * 2 - 1)
+    batch = 4
+    for (m, n, k) in [(1, 1, 8192), (3, 3, 8192), (4, 4, 6000), (12, 12, 4096), (16, 5, 4096),
+                      (4096, 3, 3), (4096, 12, 12), (3, 4096, 4), (2048, 16, 16)]:
+        # column-major batched GEMM with op(a) = a^H:  c[i,j,b] = sum_l conj(a[l,i,b]) b[l,j,b]
+        a, b = rnd(k * m * batch), rnd(k * n * batch)
+        c = torch.zeros(m * n * batch, device="cuda", dtype=tdt)
+        da, db, dc = [k, m, batch], [k, n, batch], [m, n, batch]
+        sb.contraction(1, _single(da), [0] * 3, da, da, 1, "kmb", True, [a], gpu, _single(db), [0] * 3,
+                       db, db, 1, "knb", False, [b], gpu, 0, _single(dc), [0] * 3, dc, dc, 1, "mnb", [c],
+                       gpu, sb.FastToSlow)
+        sb.sync(gpu)
+        A = a.view(batch, m, k).to(torch.complex128)   # FastToSlow: first label fastest
+        B = b.view(batch, n, k).to(torch.complex128)
+        ref = torch.einsum("bmk,bnk->bnm", A.conj(), B).contiguous().view(-1)
+        rel = (torch.linalg.norm(c.to(torch.complex128) - ref) / torch.linalg.norm(ref)).item()
+        assert rel < tol, ((m, n, k), rel)
+
+
 def test_local_contraction_wrapper(gu):
     """local_contraction (signature of the reference's tests/local.cpp:163) against the oracle."""
     import torch
