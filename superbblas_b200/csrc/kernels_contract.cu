@@ -6,8 +6,9 @@
 // never re-laid-out: every label keeps its own stride (sbk_contract_desc) and the tile loaders
 // gather straight from the caller's layout, so the permutation is fused into the GEMM.
 //
-// Two kernels:
-//  * contract_mma_kernel (double, complex double): FP64 tensor-core path.  tcgen05 has no f64 kind,
+// Kernels:
+//  * contract_mma_kernel (double, complex double; float and complex float with their tiles kept in
+//    float and widened at the fragment loads): FP64 tensor-core path.  tcgen05 has no f64 kind,
 //    so on Blackwell FP64 matrix math is issued as warp-level DMMA (mma.sync.m8n8k4.f64).  A CTA
 //    owns a 64x64 output tile of one batch entry and one K-slice; operands flow
 //    global --cp.async (16 B per complex element, any stride)--> 4-stage shared-memory ring -->
@@ -18,8 +19,11 @@
 //  * contract_reduce_kernel sums them in a fixed order (deterministic), applies alpha/beta/output
 //    strides (the reference's final add-copy, dist.h:3184, fused here).
 //  * contract_simt_kernel: any type, any shape; one thread per output element, K loop in registers,
-//    float types accumulate in double.  Used for small problems (e.g. site-wise colour-spin
-//    contractions with M=N=1) and for float / complex float.
+//    float types accumulate in double.  Used for short contractions (e.g. site-wise colour-spin
+//    contractions with M=N=1) and small tiles with many outputs.
+//  * opt-in until validated on a B200 (bodies checked on the CPU): contract_row_kernel
+//    (contract_row.hpp, short K and one small free group) and contract_dot_*_kernel
+//    (contract_dot.hpp, long K and two small free groups).
 #include "contract_dot.hpp"
 #include "contract_row.hpp"
 #include "kernels.hpp"
