@@ -48,6 +48,9 @@ typedef struct sbb_comm_s *sbb_comm_t;
 
 const char *sbb_last_error(void);
 const char *sbb_version(void);
+/** sha1 of the sources this binary was built from (the loader refuses a binary that does not match
+ *  the sources next to it) */
+const char *sbb_source_hash(void);
 /* getGpuDevicesCount (platform.h:824) */
 int sbb_device_count(int *count);
 /* sync(ctx) (blas.h:965): wait for the library stream of the context's device */

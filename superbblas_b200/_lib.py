@@ -22,6 +22,17 @@ def lib():
         _lib = ctypes.CDLL(LIB_PATH)
         _lib.sbb_last_error.restype = ctypes.c_char_p
         _lib.sbb_version.restype = ctypes.c_char_p
+        _lib.sbb_source_hash.restype = ctypes.c_char_p
+        # a binary built from other sources than the ones next to it is an error, not a warning:
+        # its ABI and kernels may differ from what the tests and the header describe
+        if os.path.isdir(os.path.join(_HERE, "csrc")) and not os.environ.get("SBB_ALLOW_STALE_LIB"):
+            from .build import source_hash
+            have, want = _lib.sbb_source_hash().decode(), source_hash()
+            if have != want:
+                _lib = None
+                raise NativeLibraryMissing(
+                    "superbblas_b200: %s was built from other sources (embedded hash %s, sources %s); "
+                    "rebuild it with `python -m superbblas_b200.build`" % (LIB_PATH, have[:12], want[:12]))
     return _lib
 
 

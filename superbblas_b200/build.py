@@ -22,7 +22,9 @@ FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-li
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
 
 
-def _stamp(path):
+def source_hash():
+    """sha1 of everything the library is built from; compiled into the .so (sbb_source_hash) so that a
+    stale binary is detected when it is loaded, whatever the file times or a stamp file say."""
     h = hashlib.sha1()
     for f in sorted(os.listdir(SRC)) + ["../../include/superbblas_b200.h"]:
         with open(os.path.join(SRC, f), "rb") as fh:
@@ -31,9 +33,22 @@ def _stamp(path):
     return h.hexdigest()
 
 
+def embedded_hash(path=None):
+    """The source hash compiled into an existing library (None if it cannot be read)."""
+    import ctypes
+    try:
+        lib = ctypes.CDLL(path or LIB)
+        lib.sbb_source_hash.restype = ctypes.c_char_p
+        return lib.sbb_source_hash().decode()
+    except (OSError, AttributeError):
+        return None
+
+
 def _compile(src):
     obj = os.path.join(OUT, src + ".o")
     cmd = [NVCC] + FLAGS + ["-c", os.path.join(SRC, src), "-o", obj]
+    if src == "capi.cpp":
+        cmd.append('-DSBB_SOURCE_HASH="%s"' % source_hash())
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
@@ -42,10 +57,7 @@ def _compile(src):
 
 def build(force=False, verbose=True):
     os.makedirs(OUT, exist_ok=True)
-    stamp_file = os.path.join(OUT, "stamp")
-    stamp = _stamp(SRC)
-    if not force and os.path.exists(LIB) and os.path.exists(stamp_file) and \
-            open(stamp_file).read() == stamp:
+    if not force and os.path.exists(LIB) and embedded_hash() == source_hash():
         return LIB
     if verbose:
         print("[superbblas_b200] compiling for sm_100a ...", file=sys.stderr)
@@ -55,8 +67,6 @@ def build(force=False, verbose=True):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    with open(stamp_file, "w") as f:
-        f.write(stamp)
     return LIB
 
 

@@ -85,7 +85,11 @@ namespace {
 extern "C" {
 
 const char *sbb_last_error(void) { return g_error.c_str(); }
-const char *sbb_version(void) { return "superbblas_b200 0.1 (sm_100a)"; }
+const char *sbb_version(void) { return "superbblas_b200 0.2 (sm_100a)"; }
+#ifndef SBB_SOURCE_HASH
+#define SBB_SOURCE_HASH "unknown"
+#endif
+const char *sbb_source_hash(void) { return SBB_SOURCE_HASH; }
 
 int sbb_device_count(int *count) {
     SBB_TRY({

@@ -46,8 +46,9 @@ namespace sbb {
     /// kernels) spins until all `nranks` slots of this rank's flag array have reached `seq`.
     void launch_signal(unsigned long long *const *peer_flags, int me, int nranks,
                        unsigned long long seq, cudaStream_t stream);
+    /// The spin is bounded by `timeout_ns`; on expiry the missing rank + 1 is written to `*error`.
     void launch_wait(const unsigned long long *flags, int nranks, unsigned long long seq,
-                     cudaStream_t stream);
+                     cudaStream_t stream, unsigned long long timeout_ns, int *error);
 
     /// Exchange signal fused into a pack kernel: the last CTA of the kernel to finish stores `sig_seq`
     /// into slot `me` of every rank's flag array (`done` counts finished CTAs and is left at zero).

@@ -1156,15 +1156,29 @@ namespace sbb {
                 asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
             }
         }
-        /// Before the unpack kernels of a round: wait until every rank has raised its flag to `seq`
-        __global__ void wait_kernel(const unsigned long long *flags, int nranks, unsigned long long seq) {
+        /// Before the unpack kernels of a round: wait until every rank has raised its flag to `seq`.
+        /// The spin is bounded: after `timeout_ns` without the flags the kernel gives up and writes the
+        /// missing rank + 1 to `*error` (host-mapped), which the next library call turns into an
+        /// exception instead of a wedged GPU.
+        __global__ void wait_kernel(const unsigned long long *flags, int nranks, unsigned long long seq,
+                                    unsigned long long timeout_ns, int *error) {
             const int r = threadIdx.x;
             if (r < nranks) {
-                unsigned long long v;
+                unsigned long long v, t0 = 0;
+                unsigned spins = 0;
                 for (;;) { // relaxed polling (served by L2, where the peers' stores land); one fence at the end
                     asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
                     if (v >= seq) break;
                     __nanosleep(100);
+                    if ((++spins & 1023u) == 0) {
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > timeout_ns) {
+                            if (error) *(volatile int *)error = r + 1;
+                            break;
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -1180,8 +1194,9 @@ namespace sbb {
     }
 
     void launch_wait(const unsigned long long *flags, int nranks, unsigned long long seq,
-                     cudaStream_t stream) {
-        wait_kernel<<<1, std::max(32, (nranks + 31) / 32 * 32), 0, stream>>>(flags, nranks, seq);
+                     cudaStream_t stream, unsigned long long timeout_ns, int *error) {
+        wait_kernel<<<1, std::max(32, (nranks + 31) / 32 * 32), 0, stream>>>(flags, nranks, seq,
+                                                                            timeout_ns, error);
         count_launch();
         cuda_check(cudaGetLastError(), "wait_kernel launch");
     }

@@ -318,15 +318,15 @@ namespace sbb {
             cudaIpcMemHandle_t mine;
             std::memset(&mine, 0, sizeof mine);
             if (ok && cudaIpcGetMemHandle(&mine, c->arena) != cudaSuccess) cudaGetLastError(), ok = 0;
-            // exchange the handles with an all-gather (they are 64 opaque bytes each)
-            char *dev = nullptr;
-            cuda_check(cudaMalloc((void **)&dev, sizeof(mine) * (c->nranks + 1)), "cudaMalloc");
+            // exchange the handles with an all-gather (they are 64 opaque bytes each); the scratch was
+            // allocated with the communicator, so nothing here can fail on one rank only before the
+            // collective (a CUDA error in these copies is sticky and fatal on every later call anyway)
+            char *dev = (char *)c->flag + 256;
             cuda_check(cudaMemcpyAsync(dev, &mine, sizeof mine, cudaMemcpyHostToDevice, d.comm_stream), "memcpy");
             nccl_check(nccl().AllGather(dev, dev + sizeof mine, sizeof mine, kNcclChar, c->nccl, d.comm_stream), "ncclAllGather");
             std::vector<cudaIpcMemHandle_t> all(c->nranks);
             cuda_check(cudaMemcpyAsync(all.data(), dev + sizeof mine, sizeof(mine) * c->nranks, cudaMemcpyDeviceToHost, d.comm_stream), "memcpy");
             cuda_check(cudaStreamSynchronize(d.comm_stream), "cudaStreamSynchronize");
-            cudaFree(dev);
             ok = agree_min(c, ok);
             c->peer.assign(c->nranks, nullptr);
             for (int r = 0; ok && r < c->nranks; ++r) {
@@ -351,8 +351,6 @@ namespace sbb {
             c->flags = (unsigned long long *)(c->arena + 2 * half_bytes);
             std::vector<unsigned long long *> pf(c->nranks);
             for (int r = 0; r < c->nranks; ++r) pf[r] = (unsigned long long *)(c->peer[r] + 2 * half_bytes);
-            if (!c->peer_flags)
-                cuda_check(cudaMalloc((void **)&c->peer_flags, sizeof(void *) * c->nranks), "cudaMalloc");
             cuda_check(cudaMemcpyAsync(c->peer_flags, pf.data(), sizeof(void *) * c->nranks,
                                        cudaMemcpyHostToDevice, d.comm_stream), "memcpy");
             cuda_check(cudaStreamSynchronize(d.comm_stream), "cudaStreamSynchronize");
@@ -370,8 +368,16 @@ namespace sbb {
             Id128 id;
             std::memcpy(id.bytes, id128, 128);
             nccl_check(nccl().CommInitRank(&c->nccl, nranks, id, rank), "ncclCommInitRank");
-            cuda_check(cudaMalloc((void **)&c->flag, 256), "cudaMalloc");
-            cuda_check(cudaMemset(c->flag, 0, 256), "cudaMemset");
+            // [0,256): barrier words and the CTA counter of the fused signal; then the scratch of the
+            // IPC handle exchange (64 bytes per rank + mine) and the table of the peers' flag arrays
+            const size_t scratch = 256 + sizeof(cudaIpcMemHandle_t) * (nranks + 1);
+            cuda_check(cudaMalloc((void **)&c->flag, scratch), "cudaMalloc");
+            cuda_check(cudaMemset(c->flag, 0, scratch), "cudaMemset");
+            cuda_check(cudaMalloc((void **)&c->peer_flags, sizeof(void *) * nranks), "cudaMalloc");
+            cuda_check(cudaHostAlloc((void **)&c->error_host, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc");
+            *c->error_host = 0;
+            cuda_check(cudaHostGetDevicePointer((void **)&c->error_dev, c->error_host, 0),
+                       "cudaHostGetDevicePointer");
             const char *e = std::getenv("SBB_P2P");
             c->p2p = !(e && std::atoi(e) == 0);
             // every rank must take the same decision
@@ -391,9 +397,35 @@ namespace sbb {
             release_arena(c);
             if (c->flag) cudaFree(c->flag);
             if (c->peer_flags) cudaFree(c->peer_flags);
+            if (c->error_host) cudaFreeHost(c->error_host);
             nccl().CommDestroy(c->nccl);
         }
         delete c;
+    }
+
+    void comm_check(Comm *c) {
+        if (!c || !c->nccl) return;
+        if (c->error_host && *(volatile int *)c->error_host != 0) {
+            c->poisoned = true;
+            throw std::runtime_error("exchange timed out waiting for rank " +
+                                     std::to_string(*(volatile int *)c->error_host - 1) +
+                                     " (its flag never arrived); the communicator is unusable");
+        }
+        if (c->poisoned)
+            throw std::runtime_error("the communicator is unusable after an earlier error inside an "
+                                     "exchange (ranks no longer agree on its state); create a new one");
+    }
+
+    namespace {
+        unsigned long long wait_timeout_ns() {
+            static unsigned long long v = 0;
+            if (!v) {
+                const char *e = std::getenv("SBB_WAIT_TIMEOUT_S");
+                const double s = e ? std::atof(e) : 60.0;
+                v = (unsigned long long)((s > 0 ? s : 60.0) * 1e9);
+            }
+            return v;
+        }
     }
 
     int64_t exchange_chunk_bytes() {
@@ -447,6 +479,32 @@ namespace sbb {
             return d;
         }
 
+        /// Pool blocks of one call: returned to the pool when the call ends, normally or not
+        struct PoolGuard {
+            std::vector<std::pair<int, void *>> blocks;
+            void *alloc(int device, size_t bytes) {
+                void *p = pool_alloc(device, bytes);
+                blocks.emplace_back(device, p);
+                return p;
+            }
+            ~PoolGuard() {
+                for (auto &b : blocks) pool_free(b.first, b.second);
+            }
+        };
+
+        /// An exception between the first and the last step of an exchange leaves this rank's view
+        /// of the communicator (arena half, sequence numbers) ahead of or behind the other ranks'
+        struct ExchangeGuard {
+            Comm *comm;
+            bool armed = true;
+            explicit ExchangeGuard(Comm *c) : comm(c) {}
+            ~ExchangeGuard() {
+                set_grid_cap(0);
+                set_exchange_sync(nullptr);
+                if (armed && comm) comm->poisoned = true;
+            }
+        };
+
         struct Resolved {
             char *ptr = nullptr;
             int device = 0;
@@ -462,6 +520,8 @@ namespace sbb {
                       const std::vector<Buffer> &v1, Comm *comm,
                       const std::vector<Buffer> *mask_a, const std::vector<Buffer> *mask_b) {
         set_exchange_sync(nullptr); // nothing left over from a call that ended with an exception
+        set_grid_cap(0);
+        comm_check(comm);
         // a rank without work still takes part in the barrier of the peer-memory transport
         if (plan.ops.empty() && !(comm && comm->nccl && comm->p2p && plan.any_comm)) return;
         const int es0 = dtype_bytes(dtype0), es1 = dtype_bytes(dtype1);
@@ -475,6 +535,7 @@ namespace sbb {
         if (plan.needs_comm && (!comm || !comm->nccl))
             throw std::runtime_error("copy needs communication but no communicator was given");
 
+        PoolGuard pool;
         // Which components take part, and how much of every destination is overwritten
         std::vector<Resolved> s(v0.size()), d(v1.size());
         std::vector<int64_t> written(v1.size(), 0);
@@ -503,7 +564,7 @@ namespace sbb {
             if (v0[c].host) {
                 s[c].host = v0[c].ptr;
                 s[c].device = home;
-                s[c].staged = pool_alloc(home, s[c].bytes);
+                s[c].staged = pool.alloc(home, s[c].bytes);
                 s[c].ptr = (char *)s[c].staged;
                 use_device(home);
                 cuda_check(cudaMemcpyAsync(s[c].ptr, v0[c].ptr, s[c].bytes, cudaMemcpyHostToDevice,
@@ -523,7 +584,7 @@ namespace sbb {
             if (v1[c].host) {
                 d[c].host = v1[c].ptr;
                 d[c].device = home;
-                d[c].staged = pool_alloc(home, d[c].bytes);
+                d[c].staged = pool.alloc(home, d[c].bytes);
                 d[c].ptr = (char *)d[c].staged;
                 // keep what the copy does not overwrite (Copy ops never overlap, see plan.cpp)
                 if (args.add || written[c] < vol || mask_a || mask_b) {
@@ -542,7 +603,6 @@ namespace sbb {
         // Masks of the destination components (MaskType = float, laid out like the component): host
         // masks are staged next to the component's data
         std::vector<const float *> mA(v1.size(), nullptr), mB(v1.size(), nullptr);
-        std::vector<std::pair<int, void *>> mask_staged;
         for (int which = 0; which < 2; ++which) {
             const std::vector<Buffer> *m = which ? mask_b : mask_a;
             if (!m) continue;
@@ -554,12 +614,11 @@ namespace sbb {
                 const float *ptr = (const float *)b.ptr;
                 if (b.host) {
                     const size_t bytes = d[c].bytes / es1 * sizeof(float);
-                    void *st = pool_alloc(d[c].device, bytes);
+                    void *st = pool.alloc(d[c].device, bytes);
                     use_device(d[c].device);
                     cuda_check(cudaMemcpyAsync(st, b.ptr, bytes, cudaMemcpyHostToDevice,
                                                device_state(d[c].device).stream),
                                "cudaMemcpyAsync H2D (mask)");
-                    mask_staged.emplace_back(d[c].device, st);
                     ptr = (const float *)st;
                 } else {
                     enable_peer(d[c].device, b.device);
@@ -593,6 +652,7 @@ namespace sbb {
 
         // Peer-memory transport: all ranks take the same decision from plan-wide quantities
         const bool p2p = comm && comm->nccl && comm->p2p && plan.any_comm;
+        ExchangeGuard exchange_guard(p2p || plan.needs_comm ? comm : nullptr);
         if (p2p) ensure_arena(comm, (size_t)plan.arena_elems * esw);
         const bool use_p2p = p2p && comm->p2p; // ensure_arena may have disabled it (collectively)
 
@@ -604,8 +664,8 @@ namespace sbb {
                 seg_send[r + 1] = seg_send[r] + ((size_t)plan.send_elems[r] * esw + 255) / 256 * 256;
                 seg_recv[r + 1] = seg_recv[r] + ((size_t)plan.recv_elems[r] * esw + 255) / 256 * 256;
             }
-            if (seg_send[plan.nranks]) sendbuf = (char *)pool_alloc(home, seg_send[plan.nranks]);
-            if (seg_recv[plan.nranks]) recvbuf = (char *)pool_alloc(home, seg_recv[plan.nranks]);
+            if (seg_send[plan.nranks]) sendbuf = (char *)pool.alloc(home, seg_send[plan.nranks]);
+            if (seg_recv[plan.nranks]) recvbuf = (char *)pool.alloc(home, seg_recv[plan.nranks]);
         }
 
         // Optional DMA variant of the peer-memory exchange (SBB_P2P_DMA_MB = message size in MB from
@@ -626,7 +686,7 @@ namespace sbb {
             if (dma) {
                 for (int r = 0; r < plan.nranks; ++r)
                     seg_send[r + 1] = seg_send[r] + ((size_t)plan.send_elems[r] * esw + 255) / 256 * 256;
-                if (seg_send[plan.nranks]) sendbuf = (char *)pool_alloc(home, seg_send[plan.nranks]);
+                if (seg_send[plan.nranks]) sendbuf = (char *)pool.alloc(home, seg_send[plan.nranks]);
             }
         }
         std::vector<char *> p2p_send_base(plan.nranks, nullptr), p2p_recv_base(plan.nranks, nullptr);
@@ -822,6 +882,11 @@ namespace sbb {
                     // my stores of this round are complete (stream order): tell every rank
                     if (!signalled)
                         launch_signal(comm->peer_flags, comm->rank, comm->nranks, seq0 + k + 1, hs.stream);
+                    // the wait kernel of this round may only become resident once my own packs are
+                    // done: queued without this dependency it would sit on an SM through whatever
+                    // long kernel precedes the pack on the compute stream (a contraction whose grid
+                    // is an exact number of waves then needs one wave more)
+                    cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
                 } else {
                     cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
                     cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
@@ -843,7 +908,9 @@ namespace sbb {
                     // local part, so that the unpack kernels only wait for an event that is normally
                     // already complete when the auxiliary stream gets there.
                     use_device(home);
-                    launch_wait(comm->flags, comm->nranks, seq0 + k + 1, hs.comm_stream);
+                    if (!dma) cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
+                    launch_wait(comm->flags, comm->nranks, seq0 + k + 1, hs.comm_stream,
+                                wait_timeout_ns(), comm->error_dev);
                     cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
                 }
                 for (int a : devs) {
@@ -972,11 +1039,7 @@ namespace sbb {
             use_device(home);
             cuda_check(cudaStreamSynchronize(hs.stream), "cudaStreamSynchronize");
         }
-        for (auto &m : mask_staged) pool_free(m.first, m.second);
-        for (auto &r : s) pool_free(home, r.staged);
-        for (auto &r : d) pool_free(home, r.staged);
-        pool_free(home, sendbuf);
-        pool_free(home, recvbuf);
+        exchange_guard.armed = false;
     }
 
 } // namespace sbb

@@ -50,7 +50,15 @@ namespace sbb {
         unsigned long long seq = 0;              ///< rounds signalled so far (all ranks agree)
         unsigned long long *flags = nullptr;     ///< my slots (inside my arena allocation)
         unsigned long long **peer_flags = nullptr; ///< device array: every rank's slots as mapped here
+        // Failure handling: a wait kernel that gives up (SBB_WAIT_TIMEOUT_S, default 60 s) writes the
+        // missing rank + 1 here (pinned host memory mapped into the device); an exception inside an
+        // exchange poisons the communicator, because the ranks no longer agree on epoch / seq.
+        int *error_host = nullptr, *error_dev = nullptr;
+        bool poisoned = false;
     };
+
+    /// Throws when the communicator is poisoned or one of its wait kernels timed out
+    void comm_check(Comm *c);
 
     void nccl_unique_id(void *id128);
     Comm *comm_create(const void *id128, int nranks, int rank, int device);
