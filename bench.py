@@ -165,6 +165,27 @@ def cpu_copy_sample(reps=5):
             "sample": "16^3 x 32 x 4 x 3 complex double (25 MB), warm (index vectors cached)"}
 
 
+def reference_gpu_comparator():
+    """The unmodified reference in CUDA mode (thrust + cuBLAS, built for sm_100 by oracle/Makefile)
+    timed on this GPU on the bench shapes: the bar SURVEY §2.1 sets ("beat thrust + cuBLAS on the
+    same B200").  Runs in a process of its own; returns its JSON or {"unavailable": why}."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu_bench")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/ref_gpu_bench is not built (make -C oracle where /root/reference exists)"}
+    blasdir = os.environ.get(
+        "SBREF_BLASDIR", "/opt/prime-rl/.venv/lib/python3.12/site-packages/opencv_python_headless.libs")
+    env = dict(os.environ, LD_LIBRARY_PATH=blasdir + ":" + os.environ.get("LD_LIBRARY_PATH", ""),
+               OMP_NUM_THREADS="1")
+    try:
+        out = subprocess.run([exe, "--reps=5"], capture_output=True, text=True, timeout=300, env=env)
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if not line:
+            return {"unavailable": "no output (rc %d): %s" % (out.returncode, out.stderr[-200:])}
+        return json.loads(line[-1])
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -483,6 +504,11 @@ def main():
         rf = torch.zeros(nout, device=dev, dtype=torch.complex64)
         stepf = lambda: contraction_step(E, head, pv, pr, af, bf, rf, gpu)  # noqa: E731
         ms_f = timed(stepf, 10, 3)
+        sb.profile_enable(True)
+        sb.profile_read("contract_tc")
+        timed(stepf, 10, 1)
+        kms_f, kn_f = sb.profile_read("contract_tc")
+        sb.profile_enable(False)
         ref0f = (B0 @ A0.conj().T)
         got0f = rf.view(NV, NV, LT)[:, :, 0].to(torch.complex128)
         err_f = float((torch.linalg.norm(got0f - ref0f) / torch.linalg.norm(ref0f)).item())
@@ -490,8 +516,11 @@ def main():
         hbm_floor_ms = min_bytes / 6545.3e9 * 1e3
         contraction_c64 = {"TFLOP/s": head.flop * 10 / (ms_f * 1e-3) / 1e12, "ms": ms_f / 10,
                            "rel_err_vs_c128": err_f, "min_bytes": min_bytes,
+                           "kernel": "contract_tc_kernel (TMA + tcgen05 kind::tf32 x3, TMEM accumulators)",
+                           "kernel_ms": kms_f / max(kn_f, 1),
                            "hbm_floor_ms": hbm_floor_ms,
-                           "frac_of_hbm_roofline": hbm_floor_ms / (ms_f / 10)}
+                           "frac_of_hbm_roofline": hbm_floor_ms / (ms_f / 10),
+                           "kernel_frac_of_hbm_roofline": hbm_floor_ms / (kms_f / max(kn_f, 1)) if kn_f else None}
         checks["contraction_c64"] = bool(err_f < 1e-5)
         del af, bf, rf
 
@@ -548,6 +577,13 @@ def main():
         except Exception as e:  # noqa: BLE001
             extras["cpu_reference_permute_xyztsc_cstzyx_c128"] = {"unavailable": str(e)}
 
+    # ---- the reference's own GPU path on this GPU (N=1 only; our tensors are freed by now) ----------------------
+    reference_gpu = None
+    if world == 1 and not args.no_extras and not args.no_cpu:
+        torch.cuda.empty_cache()
+        sb.clearCaches()
+        reference_gpu = reference_gpu_comparator()
+
     # ---- CPU baseline (rank 0, N=1 only) -----------------------------------------------------------------
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
@@ -595,6 +631,7 @@ def main():
             "host_cpus_bound_to_gpu_numa": host_affinity,
             ("strong_config4" if args.config == 2 else "weak_config2"): other_block,
             "reshuffle_summary": summary, "reshuffle": extras, "contraction_c64": contraction_c64,
+            "reference_gpu": reference_gpu,
             "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src,
         }
         print(json.dumps(line))

@@ -16,7 +16,7 @@ SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT, "libsuperbblas_b200.so")
 SOURCES = ["geometry.cpp", "plan.cpp", "contract_plan.cpp", "runtime.cpp", "capi.cpp",
-           "kernels_copy.cu", "kernels_contract.cu"]
+           "kernels_copy.cu", "kernels_contract.cu", "kernels_contract_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]

@@ -3,11 +3,14 @@
 // problems are bound by reading both operands once; the tensor-core kernel wastes most of its 64x64
 // tile on them and the generic kernel has no parallelism over K.  Here the contracted range is cut in
 // `slices` interleaved slices (consecutive threads take consecutive k, so the loads are coalesced when
-// K is contiguous); a thread keeps a 4x4 block of partial sums in registers, writes it to a workspace,
-// and a second pass sums the slices in a fixed order (deterministic) and applies alpha, beta.
+// K is contiguous); a thread keeps a 4x4 block of partial sums in registers; the 128 threads of a CTA
+// (128 consecutive slices of the same outputs) add their blocks with a fixed shuffle / shared-memory
+// tree and write ONE block per CTA to the workspace; a second pass sums the remaining slices/128
+// blocks in a fixed order (deterministic) and applies alpha, beta.
 //
-// Both passes are host/device functions: tests/test_row_kernel_emulation.py runs them thread by
-// thread on the CPU against numpy.  Status: opt-in (SBB_DOT_KERNEL=1) until validated on a B200.
+// The per-thread parts are host/device functions: tests/test_row_kernel_emulation.py runs them
+// thread by thread on the CPU against numpy (the CTA tree is emulated there by summing 128
+// consecutive threads).  Validated on a B200 in round 2 (tests/test_gpu_contraction.py).
 #pragma once
 #include "contract_row.hpp"
 
@@ -18,6 +21,7 @@ namespace sbb {
         constexpr int GD = SBK_MAX_GROUP_DIMS;
         constexpr int FMAX = 16; // largest free group
         constexpr int SB = 4;    // a thread owns an SB x SB block of outputs
+        constexpr int CTA = 128; // threads per CTA of the first pass = slices added inside a CTA
 
         struct DotParams {
             int nd_t;                                 ///< batch dims (first fastest)
@@ -41,9 +45,9 @@ namespace sbb {
 
         /// Pass 1, one thread: partial sums of its k slice for its SB x SB block
         template <typename T>
-        SBB_HD void dot_partial(const DotParams &p, long long thread, const T *va, const T *vb,
-                                typename Acc<T>::type *ws) {
-            using A = typename Acc<T>::type;
+        SBB_HD void dot_partial_acc(const DotParams &p, long long thread, const T *va, const T *vb,
+                                    typename rowk::Fast<T>::type (&acc)[SB][SB]) {
+            using A = typename rowk::Fast<T>::type;
             const int slice = (int)(thread % p.slices);
             long long rem = thread / p.slices;
             const int pg = (int)(rem % (p.pgm * p.pgn));
@@ -56,7 +60,6 @@ namespace sbb {
                 t /= p.size_t_[d];
                 oa += c * p.sa_t[d], ob += c * p.sb_t[d];
             }
-            A acc[SB][SB];
 #pragma unroll
             for (int i = 0; i < SB; ++i)
 #pragma unroll
@@ -80,7 +83,7 @@ namespace sbb {
                 for (int i = 0; i < SB; ++i) {
                     rowk::set_zero(a[i]);
                     if (m0 + i < p.m) {
-                        a[i] = rowk::widen(va[oa + ka + p.moff_a[m0 + i]]);
+                        a[i] = va[oa + ka + p.moff_a[m0 + i]];
                         if (p.conj_a) a[i] = rowk::cj(a[i]);
                     }
                 }
@@ -88,7 +91,7 @@ namespace sbb {
                 for (int j = 0; j < SB; ++j) {
                     rowk::set_zero(b[j]);
                     if (n0 + j < p.n) {
-                        b[j] = rowk::widen(vb[ob + kb + p.noff_b[n0 + j]]);
+                        b[j] = vb[ob + kb + p.noff_b[n0 + j]];
                         if (p.conj_b) b[j] = rowk::cj(b[j]);
                     }
                 }
@@ -97,12 +100,25 @@ namespace sbb {
 #pragma unroll
                     for (int j = 0; j < SB; ++j) rowk::fma_acc(acc[i][j], a[i], b[j]);
             }
-            A *out = ws + thread * (SB * SB);
+        }
+
+        /// Pass 1 without the CTA tree (slices not a multiple of 128): every thread writes its block
+        template <typename T>
+        SBB_HD void dot_partial(const DotParams &p, long long thread, const T *va, const T *vb,
+                                typename Acc<T>::type *ws) {
+            typename rowk::Fast<T>::type acc[SB][SB];
+            dot_partial_acc<T>(p, thread, va, vb, acc);
+            typename Acc<T>::type *out = ws + thread * (SB * SB);
 #pragma unroll
             for (int i = 0; i < SB; ++i)
 #pragma unroll
-                for (int j = 0; j < SB; ++j) out[i * SB + j] = acc[i][j];
+                for (int j = 0; j < SB; ++j) out[i * SB + j] = rowk::widen(acc[i][j]);
         }
+
+        /// True when every CTA of the first pass holds 128 slices of one block of outputs, so that
+        /// the CTA adds them itself; the workspace then holds slices / 128 blocks per output block
+        SBB_HD bool cta_tree(const DotParams &p) { return p.slices % CTA == 0; }
+        SBB_HD int ws_slices(const DotParams &p) { return cta_tree(p) ? p.slices / CTA : p.slices; }
 
         /// Pass 2, one thread per output: sum of the slices in order, alpha, beta, result strides
         template <typename T>
@@ -114,10 +130,11 @@ namespace sbb {
             const int mm = (int)(rem % p.m);
             long long t = rem / p.m;
             const int pg = (mm / SB) * p.pgn + nn / SB;
-            const A *src = ws + ((t * (p.pgm * p.pgn) + pg) * (long long)p.slices) * (SB * SB) +
+            const int nsl = ws_slices(p);
+            const A *src = ws + ((t * (p.pgm * p.pgn) + pg) * (long long)nsl) * (SB * SB) +
                            (mm % SB) * SB + nn % SB;
             A acc = src[0];
-            for (int s = 1; s < p.slices; ++s) acc = rowk::addc(acc, src[(long long)s * (SB * SB)]);
+            for (int s = 1; s < nsl; ++s) acc = rowk::addc(acc, src[(long long)s * (SB * SB)]);
             long long orr = p.moff_r[mm] + p.noff_r[nn];
 #pragma unroll 1
             for (int d = 0; d < p.nd_t; ++d) {
@@ -178,6 +195,7 @@ namespace sbb {
             if (s < 32) s = 32;
             if (s > 8192) s = 8192;
             if (s > p.kvol) s = p.kvol;
+            if (s >= CTA) s = s / CTA * CTA; // whole CTAs per block of outputs (see cta_tree)
             p.slices = (int)s;
         }
 

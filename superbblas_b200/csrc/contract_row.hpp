@@ -46,6 +46,25 @@ namespace sbb {
         template <> struct Acc<float> { using type = double; };
         template <> struct Acc<float2> { using type = double2; };
 
+        /// Type of the products and of the short sums a thread keeps in registers: the operand type
+        /// itself (float types stay float: at most KMAX terms per sum here, and slices of a few dozen
+        /// terms in the dot kernel; alpha, beta and the sums over slices are done in Acc<T>)
+        template <typename T> struct Fast { using type = T; };
+        SBB_HD float cj(float x) { return x; }
+        SBB_HD float2 cj(float2 x) {
+            x.y = -x.y;
+            return x;
+        }
+        SBB_HD void fma_acc(float &acc, float a, float b) { acc = fmaf(a, b, acc); }
+        SBB_HD void fma_acc(float2 &acc, float2 a, float2 b) {
+            acc.x = fmaf(a.x, b.x, acc.x);
+            acc.x = fmaf(-a.y, b.y, acc.x);
+            acc.y = fmaf(a.x, b.y, acc.y);
+            acc.y = fmaf(a.y, b.x, acc.y);
+        }
+        SBB_HD void set_zero(float &x) { x = 0; }
+        SBB_HD void set_zero(float2 &x) { x.x = x.y = 0; }
+
         SBB_HD double widen(float x) { return (double)x; }
         SBB_HD double widen(double x) { return x; }
         SBB_HD double2 widen(float2 x) {
@@ -98,26 +117,36 @@ namespace sbb {
                 rem /= p.size[d];
                 oa += c * p.sa[d], ob += c * p.sb[d], orr += c * p.sr[d];
             }
-            A acc[SMAX];
+            using F = typename Fast<T>::type;
+            F acc[SMAX];
 #pragma unroll
             for (int s = 0; s < SMAX; ++s) set_zero(acc[s]);
-#pragma unroll 4
-            for (int k = 0; k < p.nk; ++k) { // unrolled so that several loads of the row are in flight
-                A a = widen(va[oa + p.koff_a[k]]);
-                if (p.conj_a) a = cj(a);
-                const T *bk = vb + ob + p.koff_b[k];
+            constexpr int KB = 8; // loads of the row in flight per thread
+            for (int k0 = 0; k0 < p.nk; k0 += KB) {
+                F a[KB];
 #pragma unroll
-                for (int s = 0; s < SMAX; ++s)
-                    if (s < p.ns) {
-                        A b = widen(bk[p.soff_b[s]]);
-                        if (p.conj_b) b = cj(b);
-                        fma_acc(acc[s], a, b);
+                for (int j = 0; j < KB; ++j)
+                    if (k0 + j < p.nk) {
+                        a[j] = va[oa + p.koff_a[k0 + j]];
+                        if (p.conj_a) a[j] = cj(a[j]);
+                    }
+#pragma unroll
+                for (int j = 0; j < KB; ++j)
+                    if (k0 + j < p.nk) {
+                        const T *bk = vb + ob + p.koff_b[k0 + j];
+#pragma unroll
+                        for (int s = 0; s < SMAX; ++s)
+                            if (s < p.ns) {
+                                F b = bk[p.soff_b[s]];
+                                if (p.conj_b) b = cj(b);
+                                fma_acc(acc[s], a[j], b);
+                            }
                     }
             }
 #pragma unroll
             for (int s = 0; s < SMAX; ++s)
                 if (s < p.ns) {
-                    A r = mulc(alpha, acc[s]);
+                    A r = mulc(alpha, widen(acc[s]));
                     T *w = vr + orr + p.soff_r[s];
                     if (!is_zero(beta)) r = addc(r, mulc(beta, widen(*w)));
                     narrow(r, *w);

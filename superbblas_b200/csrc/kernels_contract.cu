@@ -26,6 +26,7 @@
 //    (contract_dot.hpp, long K and two small free groups).
 #include "contract_dot.hpp"
 #include "contract_row.hpp"
+#include "contract_tc.hpp"
 #include "kernels.hpp"
 #include "runtime.hpp"
 #include <algorithm>
@@ -128,8 +129,8 @@ namespace sbb {
             const long long total = p.T.vol * p.M.vol * p.N.vol;
             for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
                  idx += (long long)gridDim.x * blockDim.x) {
-                // output enumeration: n fastest, then m, then t -- or, opt-in (SBB_SIMT_ORDER=1), the
-                // group with the smallest output stride fastest, so that the stores are coalesced
+                // output enumeration: the group with the smallest output stride fastest, so that the
+                // stores are coalesced (default order: n fastest, then m, then t)
                 long long n = idx % p.N.vol, m = (idx / p.N.vol) % p.M.vol,
                           t = idx / (p.N.vol * p.M.vol);
                 if (p.out_order[0] != 2 || p.out_order[1] != 1)
@@ -176,13 +177,42 @@ namespace sbb {
 
         // ---- dot kernel (long contraction, both free groups small; bodies in contract_dot.hpp) -------
 
+        __device__ __forceinline__ double shfl_down(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
+        __device__ __forceinline__ double2 shfl_down(double2 v, int off) {
+            return make_double2(__shfl_down_sync(0xffffffffu, v.x, off), __shfl_down_sync(0xffffffffu, v.y, off));
+        }
+
         template <typename T>
-        __global__ void __launch_bounds__(128)
+        __global__ void __launch_bounds__(dotk::CTA)
             contract_dot_partial_kernel(const __grid_constant__ dotk::DotParams p,
                                         const T *__restrict__ va, const T *__restrict__ vb,
                                         typename rowk::Acc<T>::type *__restrict__ ws) {
+            using A = typename rowk::Acc<T>::type;
+            constexpr int SB = dotk::SB;
             const long long thread = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-            if (thread < dotk::threads_of(p)) dotk::dot_partial<T>(p, thread, va, vb, ws);
+            if (!dotk::cta_tree(p)) { // few slices: every thread writes its own block
+                if (thread < dotk::threads_of(p)) dotk::dot_partial<T>(p, thread, va, vb, ws);
+                return;
+            }
+            // the CTA holds 128 slices of the same outputs: add them here (fixed tree: deterministic)
+            typename rowk::Fast<T>::type acc[SB][SB];
+            dotk::dot_partial_acc<T>(p, thread, va, vb, acc);
+            __shared__ A part[dotk::CTA / 32][SB * SB];
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+            for (int q = 0; q < SB * SB; ++q) {
+                A v = rowk::widen(acc[q / SB][q % SB]);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v = rowk::addc(v, shfl_down(v, off));
+                if (lane == 0) part[warp][q] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x < SB * SB) {
+                A v = part[0][threadIdx.x];
+#pragma unroll
+                for (int w = 1; w < dotk::CTA / 32; ++w) v = rowk::addc(v, part[w][threadIdx.x]);
+                ws[blockIdx.x * (long long)(SB * SB) + threadIdx.x] = v;
+            }
         }
 
         template <typename T>
@@ -641,7 +671,7 @@ namespace sbb {
             using A = typename Acc<T>::type;
             const long long threads = dotk::threads_of(dp);
             A *ws = (A *)pool_alloc(device, (size_t)threads * dotk::SB * dotk::SB * sizeof(A));
-            contract_dot_partial_kernel<T><<<(unsigned)((threads + 127) / 128), 128, 0, stream>>>(
+            contract_dot_partial_kernel<T><<<(unsigned)((threads + dotk::CTA - 1) / dotk::CTA), dotk::CTA, 0, stream>>>(
                 dp, (const T *)v0, (const T *)v1, ws);
             count_launch();
             cuda_check(cudaGetLastError(), "contract_dot_partial_kernel launch");
@@ -791,21 +821,35 @@ namespace sbb {
                         (p.K.vol >= 2048 && outputs < 148ll * 2048));
         if (force && std::strcmp(force, "simt") == 0) use_mma = false;
         if (force && std::strcmp(force, "mma") == 0 && p.K.vol > 0) use_mma = true;
-        // Opt-in (SBB_ROW_KERNEL=1, not yet validated on a B200; its body is checked on the CPU by
-        // tests/test_row_kernel_emulation.py): short contractions with one small free group
-        static int row_env = -1;
-        if (row_env < 0) {
-            const char *e = std::getenv("SBB_ROW_KERNEL");
-            row_env = e ? std::atoi(e) : 0;
+        // Complex float with real tiles and a long, contiguous contracted index: the tcgen05 path
+        // (TF32 x 3 split, FP32 accumulation in tensor memory; kernels_contract_tc.cu).  The FP64
+        // tensor-pipe kernel below stays the path for everything else (and SBB_CONTRACT_KERNEL=mma
+        // selects it for the accuracy comparison in the tests).
+        if (dtype == SBB_C64 && (!force || std::strcmp(force, "tc") == 0) && p.K.n == 1 &&
+            p.K.s0[0] == 1 && p.K.s1[0] == 1 && p.M.n <= 1 && p.N.n <= 1 && p.T.n <= 2 &&
+            p.K.vol >= 256 && p.M.vol >= 16 && p.N.vol >= 16 && p.M.vol < (1 << 30) && p.N.vol < (1 << 30)) {
+            tc::Problem tp;
+            std::memset(&tp, 0, sizeof tp);
+            tp.nT = p.T.n;
+            for (int d = 0; d < p.T.n; ++d)
+                tp.T[d] = tc::Dim{p.T.size[d], p.T.s0[d], p.T.s1[d], p.T.sr[d]};
+            tp.M = tc::Dim{(int)p.M.vol, p.M.n ? p.M.s0[0] : 0, 0, p.M.n ? p.M.sr[0] : 0};
+            tp.N = tc::Dim{(int)p.N.vol, 0, p.N.n ? p.N.s1[0] : 0, p.N.n ? p.N.sr[0] : 0};
+            tp.K = p.K.vol, tp.conj0 = p.conj0, tp.conj1 = p.conj1;
+            if (describe ? true : tc::eligible(tp, v0, v1)) {
+                if (!describe || tc::eligible(tp, (const void *)16, (const void *)16)) {
+                    tc::launch_c64(tp, alpha, v0, v1, beta, vr, device, stream, describe);
+                    return;
+                }
+            }
         }
-        // Opt-in (SBB_DOT_KERNEL=1, same status; bodies checked on the CPU): long contractions whose
-        // free groups are both small
-        static int dot_env = -1;
-        if (dot_env < 0) {
-            const char *e = std::getenv("SBB_DOT_KERNEL");
-            dot_env = e ? std::atoi(e) : 0;
-        }
-        if (dot_env && !force && p.K.vol >= 1024 && dotk::eligible(desc)) {
+        // Small-tile regimes (validated on a B200 in round 2; bodies also checked on the CPU by
+        // tests/test_row_kernel_emulation.py): long contractions whose free groups are both small go
+        // to the dot kernel, short contractions with one small free group to the row kernel.
+        // SBB_CONTRACT_KERNEL = simt | mma | tc | row | dot forces a path (tests).
+        const bool want_dot = force ? std::strcmp(force, "dot") == 0 : true;
+        const bool want_row = force ? std::strcmp(force, "row") == 0 : true;
+        if (want_dot && (force || p.K.vol >= 1024) && dotk::eligible(desc)) {
             dotk::DotParams dp;
             dotk::build(desc, dp, (long long)sm_count(device) * 2048);
             if (dotk::threads_of(dp) <= (1ll << 22)) {
@@ -825,7 +869,7 @@ namespace sbb {
                 return;
             }
         }
-        if (row_env && !force && !use_mma && rowk::eligible(desc)) {
+        if (want_row && (force || !use_mma) && rowk::eligible(desc)) {
             rowk::RowParams rp;
             bool swapped = false;
             rowk::build(desc, rp, swapped);
@@ -904,20 +948,14 @@ namespace sbb {
         }
         p.out_order[0] = 2, p.out_order[1] = 1, p.out_order[2] = 0;
         {
-            static int simt_order = -1;
-            if (simt_order < 0) {
-                const char *e = std::getenv("SBB_SIMT_ORDER");
-                simt_order = e ? std::atoi(e) : 0;
-            }
-            if (simt_order) {
-                auto min_sr = [](const Group &g) {
-                    long long s = 1ll << 62;
-                    for (int d = 0; d < g.n; ++d) s = std::min(s, g.sr[d] < 0 ? -g.sr[d] : g.sr[d]);
-                    return s;
-                };
-                const long long key[3] = {min_sr(p.T), min_sr(p.M), min_sr(p.N)};
-                rowk::output_order(key, p.out_order);
-            }
+            // enumerate the outputs along the smallest result stride, so that the stores coalesce
+            auto min_sr = [](const Group &g) {
+                long long s = 1ll << 62;
+                for (int d = 0; d < g.n; ++d) s = std::min(s, g.sr[d] < 0 ? -g.sr[d] : g.sr[d]);
+                return s;
+            };
+            const long long key[3] = {min_sr(p.T), min_sr(p.M), min_sr(p.N)};
+            rowk::output_order(key, p.out_order);
         }
         switch (dtype) {
         case SBB_F32: launch_simt<float>(p, alpha, v0, v1, beta, vr, device, stream); break;

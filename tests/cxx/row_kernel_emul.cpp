@@ -50,9 +50,24 @@ template <typename T>
 static void run_dot(const sbb::dotk::DotParams &p, const double *alpha, const void *v0, const void *v1,
                     const double *beta, void *vr) {
     using A = typename Acc<T>::type;
-    std::vector<A> ws((size_t)sbb::dotk::threads_of(p) * sbb::dotk::SB * sbb::dotk::SB);
-    for (long long th = 0; th < sbb::dotk::threads_of(p); ++th)
-        sbb::dotk::dot_partial<T>(p, th, (const T *)v0, (const T *)v1, ws.data());
+    constexpr int SB = sbb::dotk::SB;
+    std::vector<A> ws((size_t)sbb::dotk::threads_of(p) * SB * SB);
+    if (sbb::dotk::cta_tree(p)) {
+        // what a CTA of the CUDA kernel does: its 128 threads add their blocks, one block is written
+        for (long long th = 0; th < sbb::dotk::threads_of(p); th += sbb::dotk::CTA) {
+            A sum[SB * SB];
+            for (int q = 0; q < SB * SB; ++q) set_zero(sum[q]);
+            for (int l = 0; l < sbb::dotk::CTA; ++l) {
+                typename Fast<T>::type acc[SB][SB];
+                sbb::dotk::dot_partial_acc<T>(p, th + l, (const T *)v0, (const T *)v1, acc);
+                for (int q = 0; q < SB * SB; ++q) sum[q] = addc(sum[q], widen(acc[q / SB][q % SB]));
+            }
+            for (int q = 0; q < SB * SB; ++q) ws[(size_t)(th / sbb::dotk::CTA) * SB * SB + q] = sum[q];
+        }
+    } else {
+        for (long long th = 0; th < sbb::dotk::threads_of(p); ++th)
+            sbb::dotk::dot_partial<T>(p, th, (const T *)v0, (const T *)v1, ws.data());
+    }
     for (long long o = 0; o < sbb::dotk::outputs_of(p); ++o)
         sbb::dotk::dot_reduce<T>(p, o, ws.data(), (T *)vr, scalar<T>(alpha), scalar<T>(beta));
 }

@@ -171,6 +171,64 @@ def test_skinny_shapes_of_the_reference_dist_program(gu, dtype):
         assert rel < tol, ((m, n, k), rel)
 
 
+@pytest.mark.parametrize("shape", [
+    # (m, n, k, batch dims, conj0, conj1, alpha, beta)
+    (64, 64, 1536, (4,), True, False, 1, 0),            # the distillation tile, whole
+    (20, 50, 1000, (3, 2), False, False, 0.5 - 2j, 1.5 + 0.5j),  # partial tiles, K tail, two batch dims
+    (130, 70, 2048 + 8, (2,), False, True, -1, 0),      # several tiles per batch entry
+    (64, 64, 4 * 32 * 37, (1,), True, True, 1, 1),      # no batch dim, long K (deep split-K)
+    (16, 16, 512, (5,), True, False, 2, 0),             # smallest eligible tile
+])
+def test_tcgen05_complex_float(gu, shape):
+    """Complex float contractions with a long contiguous K run on the tcgen05 path (TMA -> TF32 x 3
+    split -> tensor memory).  Checked against a complex128 einsum (tolerance 1e-5, the north star's
+    bound for complex float), next to the FP64 tensor-pipe kernel on the same data; the values span
+    several orders of magnitude and both signs so that the hi/lo split is exercised."""
+    import torch
+    m, n, k, bdims, conj0, conj1, alpha, beta = shape
+    gpu = sb.createGpuContext(0)
+    g = torch.Generator(device="cuda").manual_seed(m * 1000 + n)
+    nb = int(np.prod(bdims))
+
+    def rnd(count):
+        x = torch.randn(count, 2, generator=g, device="cuda", dtype=torch.float32)
+        e = torch.rand(count, 1, generator=g, device="cuda", dtype=torch.float32) * 4 - 2
+        return torch.view_as_complex((x * torch.pow(10.0, e)).contiguous())
+    blabels = "tu"[:len(bdims)]
+    da, db, dc = [k, *bdims, m], [k, *bdims, n], [*bdims, m, n]
+    oa, ob, oc = "k" + blabels + "m", "k" + blabels + "n", blabels + "mn"
+    a, b = rnd(k * nb * m), rnd(k * nb * n)
+    c0 = rnd(nb * m * n)
+    A = a.view(m, *reversed(bdims), k).reshape(m, nb, k).to(torch.complex128)  # first label fastest
+    B = b.view(n, *reversed(bdims), k).reshape(n, nb, k).to(torch.complex128)
+    ref = torch.einsum("mtk,ntk->nmt", A.conj() if conj0 else A, B.conj() if conj1 else B)
+    ref = complex(alpha) * ref + complex(beta) * c0.view(n, m, nb).to(torch.complex128)
+    errs = {}
+    for kernel in ("auto", "mma"):
+        if kernel == "auto":
+            os.environ.pop("SBB_CONTRACT_KERNEL", None)
+        else:
+            os.environ["SBB_CONTRACT_KERNEL"] = kernel
+        try:
+            c = c0.clone()
+            sb.profile_enable(True)
+            sb.profile_read("contract_tc")
+            sb.contraction(alpha, _single(da), [0] * len(da), da, da, 1, oa, conj0, [a], gpu,
+                           _single(db), [0] * len(db), db, db, 1, ob, conj1, [b], gpu, beta,
+                           _single(dc), [0] * len(dc), dc, dc, 1, oc, [c], gpu, sb.FastToSlow)
+            sb.sync(gpu)
+            _, launched = sb.profile_read("contract_tc")
+            sb.profile_enable(False)
+        finally:
+            os.environ.pop("SBB_CONTRACT_KERNEL", None)
+        assert (launched >= 1) == (kernel == "auto"), (kernel, launched)
+        got = c.view(n, m, nb).to(torch.complex128)
+        errs[kernel] = (torch.linalg.norm(got - ref) / torch.linalg.norm(ref)).item()
+    print("tcgen05 c64 %s: rel err %.2e (FP64-pipe kernel %.2e)" % (shape[:4], errs["auto"], errs["mma"]))
+    assert errs["auto"] < 1e-5, errs
+    assert errs["mma"] < 1e-5, errs
+
+
 def test_local_contraction_wrapper(gu):
     """local_contraction (signature of the reference's tests/local.cpp:163) against the oracle."""
     import torch
