@@ -39,6 +39,7 @@
 #include <chrono>
 #include <complex>
 #include <cstring>
+#include <cstdlib>
 #include <functional>
 #include <iostream>
 #include <map>
@@ -396,7 +397,15 @@ namespace superbblas {
     }
 
     // Diagnostics of the reference that callers and its tests reference; cheap no-ops here
-    inline int getDebugLevel() { return 0; }
+    /// SB_DEBUG (runtime_features.h:31): 0 = none; >= 2 makes every copy verify itself on
+    /// index-valued mock tensors first (dist.h:2282-2285), which the library does in sbb_copy
+    inline int getDebugLevel() {
+        static int level = [] {
+            const char *e = std::getenv("SB_DEBUG");
+            return e ? std::atoi(e) : 0;
+        }();
+        return level;
+    }
     inline void resetTimings() {}
     template <typename OStream> void reportTimings(OStream &) {}
     template <typename OStream> void reportCacheUsage(OStream &) {}
@@ -495,6 +504,30 @@ namespace superbblas {
         detail::check_order<Nd0>(o0, "o0");
         detail::check_order<Nd1>(o1, "o1");
         const auto a = detail::scalar(alpha);
+        if (request) {
+            // deferred completion (dist.h:3554-3557): the packs, their signal and the local part are
+            // queued now; wait(request) queues the unpack side and completes host destinations
+            sbb_request_t h = nullptr;
+            detail::check(sbb_copy_begin(detail::dtype_of<T>::value, detail::dtype_of<Q>::value, a.data(),
+                                         (int)Nd0, (const int *)p0, ncomponents0, o0, from0.data(),
+                                         size0.data(), dim0.data(), (const void *const *)v0,
+                                         (const float *const *)mask0, detail::ctx_ptr(ctx0), (int)Nd1,
+                                         (const int *)p1, ncomponents1, o1, from1.data(), dim1.data(),
+                                         (void *const *)v1, (const float *const *)mask1,
+                                         detail::ctx_ptr(ctx1), comm, co == SlowToFast ? 0 : 1,
+                                         copyadd == Copy ? 0 : 1, &h));
+            // the std::function may be copied: the handle is completed (and released) exactly once
+            std::shared_ptr<sbb_request_t> once(new sbb_request_t(h), [](sbb_request_t *q) {
+                if (*q) sbb_request_wait(*q); // dropped without wait: complete it anyway
+                delete q;
+            });
+            *request = [once]() {
+                sbb_request_t q = *once;
+                *once = nullptr;
+                if (q) detail::check(sbb_request_wait(q));
+            };
+            return;
+        }
         detail::check(sbb_copy(detail::dtype_of<T>::value, detail::dtype_of<Q>::value, a.data(),
                                (int)Nd0, (const int *)p0, ncomponents0, o0, from0.data(),
                                size0.data(), dim0.data(), (const void *const *)v0,
@@ -503,7 +536,6 @@ namespace superbblas {
                                (void *const *)v1, (const float *const *)mask1,
                                detail::ctx_ptr(ctx1), comm, co == SlowToFast ? 0 : 1,
                                copyadd == Copy ? 0 : 1));
-        if (request) *request = Request{};
     }
 
     /// No-communicator overload (reference: dist.h:3583)

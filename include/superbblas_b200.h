@@ -43,6 +43,8 @@ typedef struct sbb_context {
  * communicator is one NCCL rank bound to one GPU; partitions then have nranks*ncomponents items,
  * ordered [rank][component] exactly like the reference (dist.h:3252-3261). */
 typedef struct sbb_comm_s *sbb_comm_t;
+/* A copy that has been begun and not completed (the reference's Request, dist.h:54-61) */
+typedef struct sbb_request_s *sbb_request_t;
 
 /* ---- library ----------------------------------------------------------------------------------- */
 
@@ -85,6 +87,14 @@ int sbb_profile_read(const char *kernel, double *total_ms, long long *count);
 /* Write a 128-byte NCCL unique id (rank 0 calls it and broadcasts the bytes by any means) */
 int sbb_comm_unique_id(void *id128);
 int sbb_comm_create(const void *id128, int nranks, int rank, int device, sbb_comm_t *comm);
+/* `nranks` "loopback" communicators whose ranks all live in THIS process (rank r works on
+ * devices[r]; devices may repeat).  The exchange is the same as between processes -- pack kernels
+ * store into the receiver's arena, unpack kernels read it -- with CUDA events for the
+ * synchronisation.  One host thread drives the ranks in phases: every rank begins a copy
+ * (sbb_copy_begin), then every rank completes it (sbb_request_wait); completing a copy before every
+ * rank has begun it is an error.  Masked copies are not supported on loopback communicators.
+ * This is how the cross-rank path is tested on a box with fewer GPUs than ranks. */
+int sbb_comm_create_local(int nranks, const int *devices, sbb_comm_t *comms);
 int sbb_comm_destroy(sbb_comm_t comm);
 int sbb_comm_rank(sbb_comm_t comm, int *rank, int *nranks);
 
@@ -126,6 +136,22 @@ int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0
              const int *p1, int ncomponents1, const char *o1, const int *from1, const int *dim1,
              void *const *v1, const float *const *mask1, const sbb_context *ctx1, sbb_comm_t comm,
              int co, int copyadd);
+
+/* The same copy in two steps (reference: the `Request *request` argument of copy, dist.h:3534-3558,
+ * and wait(request), dist.h:61).  sbb_copy_begin queues everything that does not depend on other
+ * ranks (staging of host components, pack kernels and their signal, the local part) and returns;
+ * sbb_request_wait queues the rest (wait for the other ranks' data, unpack kernels), copies host
+ * destinations back and returns when those are complete.  The request is released by the wait
+ * whatever its outcome.  Sources must not be modified and destinations not be read in between.  A
+ * communicator carries one outstanding copy at a time: beginning another one completes it first. */
+int sbb_copy_begin(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0,
+                   int ncomponents0, const char *o0, const int *from0, const int *size0,
+                   const int *dim0, const void *const *v0, const float *const *mask0,
+                   const sbb_context *ctx0, int nd1, const int *p1, int ncomponents1, const char *o1,
+                   const int *from1, const int *dim1, void *const *v1, const float *const *mask1,
+                   const sbb_context *ctx1, sbb_comm_t comm, int co, int copyadd,
+                   sbb_request_t *request);
+int sbb_request_wait(sbb_request_t request);
 
 /* Describe, without touching any data, the operations sbb_copy would run on `rank` of `nranks`:
  * writes a text description (one op per line) into buf.  Host only; used by the CPU-side tests to

@@ -13,3 +13,4 @@ print({k:(round(v['ms'],3), round(v['GB/s']/d['n_gpus'])) for k,v in d['reshuffl
 "
 tail -5 gpurun_out/r2_bench_n$N.err
 if [ "$N" = "2" ]; then scripts/with_timeout.sh 120 scripts/micro/p2p_probe > gpurun_out/r2_p2p_probe.log 2>&1; echo "probe rc=$?"; cat gpurun_out/r2_p2p_probe.log; fi
+timeout 120 python scripts/tc_accuracy.py > gpurun_out/r2_tc_default.json 2>&1; cat gpurun_out/r2_tc_default.json | tail -1

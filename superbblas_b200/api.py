@@ -101,6 +101,32 @@ class Comm:
             self.handle = None
 
 
+class Request:
+    """A copy that has been begun (reference: Request, dist.h:54); wait() completes it."""
+
+    def __init__(self, handle, keep):
+        self.handle, self._keep = handle, keep  # the marshalled arrays live as long as the request
+
+    def wait(self):
+        h, self.handle, self._keep = self.handle, None, None
+        if h:
+            check(lib().sbb_request_wait(h))
+
+
+def wait(request):
+    request.wait()
+
+
+def comm_create_local(nranks, devices=None):
+    """`nranks` loopback communicators living in this process (tests of the cross-rank path on fewer
+    GPUs than ranks); rank r works on devices[r] (default: all on device 0)."""
+    devices = list(devices) if devices is not None else [0] * nranks
+    dv = (ctypes.c_int * nranks)(*devices)
+    hs = (ctypes.c_void_p * nranks)()
+    check(lib().sbb_comm_create_local(nranks, dv, hs))
+    return [Comm(ctypes.c_void_p(hs[r]), r, nranks) for r in range(nranks)]
+
+
 def comm_unique_id():
     buf = ctypes.create_string_buffer(128)
     check(lib().sbb_comm_unique_id(buf))
@@ -245,8 +271,9 @@ def make_hole(frm, size, hole_from, hole_size, dim):
 # --- copy ----------------------------------------------------------------------------------------
 
 def copy(alpha, p0, ncomponents0, o0, from0, size0, dim0, v0, mask0, ctx0,
-         p1, ncomponents1, o1, from1, dim1, v1, mask1, ctx1, co, copyadd, comm=None):
-    """superbblas::copy (dist.h:3583; with `comm` the MPI overload dist.h:3534)."""
+         p1, ncomponents1, o1, from1, dim1, v1, mask1, ctx1, co, copyadd, comm=None, request=False):
+    """superbblas::copy (dist.h:3583; with `comm` the MPI overload dist.h:3534).  With request=True
+    the copy is only begun and a Request is returned (the reference's `Request *request` argument)."""
     n0, n1 = len(o0), len(o1)
     pv0, dt0, k0 = _components(v0)
     pv1, dt1, k1 = _components(v1)
@@ -269,11 +296,16 @@ def copy(alpha, p0, ncomponents0, o0, from0, size0, dim0, v0, mask0, ctx0,
     nr = comm.nranks if comm else 1
     a = [_partition(p0, nr * ncomponents0, n0), _ia(from0, n0), _ia(size0, n0), _ia(dim0, n0),
          _partition(p1, nr * ncomponents1, n1), _ia(from1, n1), _ia(dim1, n1)]
-    check(lib().sbb_copy(dt0, dt1, _scalar(alpha), n0, _ip(a[0]), ncomponents0, _order(o0),
-                         _ip(a[1]), _ip(a[2]), _ip(a[3]), pv0, pm0, _contexts(ctx0, ncomponents0),
-                         n1, _ip(a[4]), ncomponents1, _order(o1), _ip(a[5]), _ip(a[6]), pv1, pm1,
-                         _contexts(ctx1, ncomponents1), comm.handle if comm else None, _co(co),
-                         int(copyadd)))
+    call = (dt0, dt1, _scalar(alpha), n0, _ip(a[0]), ncomponents0, _order(o0),
+            _ip(a[1]), _ip(a[2]), _ip(a[3]), pv0, pm0, _contexts(ctx0, ncomponents0),
+            n1, _ip(a[4]), ncomponents1, _order(o1), _ip(a[5]), _ip(a[6]), pv1, pm1,
+            _contexts(ctx1, ncomponents1), comm.handle if comm else None, _co(co), int(copyadd))
+    if not request:
+        check(lib().sbb_copy(*call))
+        return None
+    h = ctypes.c_void_p()
+    check(lib().sbb_copy_begin(*call, ctypes.byref(h)))
+    return Request(h, (call, a, k0, k1, v0, v1, mask0, mask1))
 
 
 def local_copy(alpha, o0, from0, size0, dim0, v0, mask0, ctx0, o1, from1, dim1, v1, mask1, ctx1,

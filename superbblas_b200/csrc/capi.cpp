@@ -3,6 +3,7 @@
 #include "runtime.hpp"
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 
 using namespace sbb;
@@ -192,6 +193,13 @@ int sbb_comm_create(const void *id128, int nranks, int rank, int device, sbb_com
     SBB_TRY(*comm = (sbb_comm_t)comm_create(id128, nranks, rank, device));
 }
 
+int sbb_comm_create_local(int nranks, const int *devices, sbb_comm_t *comms) {
+    SBB_TRY({
+        auto v = comm_create_local(nranks, devices);
+        for (int r = 0; r < nranks; ++r) comms[r] = (sbb_comm_t)v[r];
+    });
+}
+
 int sbb_comm_destroy(sbb_comm_t comm) { SBB_TRY(comm_destroy((Comm *)comm)); }
 
 int sbb_comm_rank(sbb_comm_t comm, int *rank, int *nranks) {
@@ -236,30 +244,30 @@ int sbb_make_hole(int nd, const int *from, const int *size, const int *hole_from
     });
 }
 
-int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0, int ncomponents0,
-             const char *o0, const int *from0, const int *size0, const int *dim0,
-             const void *const *v0, const float *const *mask0, const sbb_context *ctx0, int nd1,
-             const int *p1, int ncomponents1, const char *o1, const int *from1, const int *dim1,
-             void *const *v1, const float *const *mask1, const sbb_context *ctx1, sbb_comm_t comm,
-             int co, int copyadd) {
-    SBB_TRY({
-        Comm *c = (Comm *)comm;
+namespace {
+    /// Everything of a copy up to the executor (for masked copies that includes carrying mask0 to
+    /// the destination layout, which is a complete copy of its own)
+    std::unique_ptr<CopyExec> make_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0,
+                                        int ncomponents0, const char *o0, const int *from0,
+                                        const int *size0, const int *dim0, const void *const *v0,
+                                        const float *const *mask0, const sbb_context *ctx0, int nd1,
+                                        const int *p1, int ncomponents1, const char *o1, const int *from1,
+                                        const int *dim1, void *const *v1, const float *const *mask1,
+                                        const sbb_context *ctx1, Comm *c, int co, int copyadd) {
         // Whether a copy is masked must not depend on the rank (a rank whose components are all
         // empty passes null entries): it is decided by the mask ARRAYS being given.
         const bool has_m0 = mask0 != nullptr, has_m1 = mask1 != nullptr;
-        CopyArgs a = make_copy_args(nd0, p0, ncomponents0, o0, from0, size0, dim0, nd1, p1,
-                                    ncomponents1, o1, from1, dim1, c ? c->nranks : 1,
-                                    c ? c->rank : 0, co, copyadd);
+        CopyArgs a = make_copy_args(nd0, p0, ncomponents0, o0, from0, size0, dim0, nd1, p1, ncomponents1,
+                                    o1, from1, dim1, c ? c->nranks : 1, c ? c->rank : 0, co, copyadd);
         dtype_bytes(dtype0);
         a.alpha_is_zero = is_zero(dtype0, alpha);
         a.wire_align = 16 / dtype_bytes((a.add && dtype0 != dtype1) ? dtype0 : dtype1);
         a.chunk_bytes = exchange_chunk_bytes();
         auto plan = get_copy_plan(a);
-        if (!has_m0 && !has_m1) {
-            execute_copy(*plan, a, dtype0, dtype1, alpha, buffers(v0, ctx0, ncomponents0),
-                         buffers((const void *const *)v1, ctx1, ncomponents1), c);
-            return 0;
-        }
+        if (!has_m0 && !has_m1)
+            return std::unique_ptr<CopyExec>(new CopyExec(plan, a, dtype0, dtype1, alpha,
+                                                          buffers(v0, ctx0, ncomponents0),
+                                                          buffers((const void *const *)v1, ctx1, ncomponents1), c));
         // Masked copy (reference: tensor.h:1022-1027, dist.h:944-970, :1240-1243): an element moves
         // iff the source mask at its origin and the destination mask at its target are nonzero.
         // Step 1 carries mask0 to the destination layout with the copy engine itself (a float copy
@@ -267,6 +275,14 @@ int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0
         // a predicate on every destination store.
         std::vector<Buffer> m0b, m1b, tmp;
         if (has_m1) m1b = buffers((const void *const *)mask1, ctx1, ncomponents1);
+        struct Blocks {
+            std::vector<Buffer> *v;
+            bool armed = true;
+            ~Blocks() {
+                if (armed)
+                    for (auto &t : *v) pool_free(t.device, t.ptr);
+            }
+        } blocks{&tmp};
         if (has_m0 && !a.alpha_is_zero) {
             m0b = buffers((const void *const *)mask0, ctx0, ncomponents0);
             tmp.resize(ncomponents1);
@@ -280,23 +296,53 @@ int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0
             am.add = false;
             am.wire_align = 16 / (int)sizeof(float);
             const double one[2] = {1, 0};
-            try {
-                execute_copy(*get_copy_plan(am), am, SBB_F32, SBB_F32, one, m0b, tmp, c);
-            } catch (...) {
-                for (auto &t : tmp) pool_free(t.device, t.ptr);
-                throw;
-            }
+            execute_copy(*get_copy_plan(am), am, SBB_F32, SBB_F32, one, m0b, tmp, c);
         }
-        try {
-            execute_copy(*plan, a, dtype0, dtype1, alpha, buffers(v0, ctx0, ncomponents0),
-                         buffers((const void *const *)v1, ctx1, ncomponents1), c,
-                         tmp.empty() ? nullptr : &tmp, has_m1 ? &m1b : nullptr);
-        } catch (...) {
-            for (auto &t : tmp) pool_free(t.device, t.ptr);
-            throw;
-        }
-        for (auto &t : tmp) pool_free(t.device, t.ptr);
+        std::unique_ptr<CopyExec> e(new CopyExec(plan, a, dtype0, dtype1, alpha, buffers(v0, ctx0, ncomponents0),
+                                                 buffers((const void *const *)v1, ctx1, ncomponents1), c,
+                                                 tmp.empty() ? nullptr : &tmp, has_m1 ? &m1b : nullptr));
+        for (auto &t : tmp) e->adopt(t.device, t.ptr);
+        blocks.armed = false;
+        return e;
+    }
+}
+
+int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0, int ncomponents0,
+             const char *o0, const int *from0, const int *size0, const int *dim0,
+             const void *const *v0, const float *const *mask0, const sbb_context *ctx0, int nd1,
+             const int *p1, int ncomponents1, const char *o1, const int *from1, const int *dim1,
+             void *const *v1, const float *const *mask1, const sbb_context *ctx1, sbb_comm_t comm,
+             int co, int copyadd) {
+    SBB_TRY({
+        auto e = make_copy(dtype0, dtype1, alpha, nd0, p0, ncomponents0, o0, from0, size0, dim0, v0, mask0,
+                           ctx0, nd1, p1, ncomponents1, o1, from1, dim1, v1, mask1, ctx1, (Comm *)comm, co,
+                           copyadd);
+        e->begin();
+        e->finish();
     });
+}
+
+int sbb_copy_begin(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0,
+                   int ncomponents0, const char *o0, const int *from0, const int *size0,
+                   const int *dim0, const void *const *v0, const float *const *mask0,
+                   const sbb_context *ctx0, int nd1, const int *p1, int ncomponents1, const char *o1,
+                   const int *from1, const int *dim1, void *const *v1, const float *const *mask1,
+                   const sbb_context *ctx1, sbb_comm_t comm, int co, int copyadd,
+                   sbb_request_t *request) {
+    SBB_TRY({
+        *request = nullptr;
+        auto e = make_copy(dtype0, dtype1, alpha, nd0, p0, ncomponents0, o0, from0, size0, dim0, v0, mask0,
+                           ctx0, nd1, p1, ncomponents1, o1, from1, dim1, v1, mask1, ctx1, (Comm *)comm, co,
+                           copyadd);
+        e->begin();
+        *request = (sbb_request_t)e.release();
+    });
+}
+
+int sbb_request_wait(sbb_request_t request) {
+    if (!request) return 0;
+    std::unique_ptr<CopyExec> e((CopyExec *)request); // released whether or not the completion works
+    SBB_TRY(e->finish());
 }
 
 int sbb_copy_plan_describe(int elem_size1, int nd0, const int *p0, int ncomponents0, const char *o0,

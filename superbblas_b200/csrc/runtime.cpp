@@ -292,15 +292,40 @@ namespace sbb {
 
         void release_arena(Comm *c) {
             use_device(c->device);
-            for (int r = 0; r < (int)c->peer.size(); ++r)
-                if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+            if (!c->local)
+                for (int r = 0; r < (int)c->peer.size(); ++r)
+                    if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
             c->peer.clear();
             if (c->arena) cudaFree(c->arena);
             c->arena = nullptr, c->half_bytes = 0;
         }
 
+        /// Loopback group: all arenas grow together (one host thread owns every member)
+        void ensure_arena_local(Comm *c, size_t half_bytes) {
+            if (half_bytes <= c->half_bytes) return;
+            LocalGroup *g = c->local;
+            for (Comm *m : g->members) { // nobody may still be using the old arenas
+                use_device(m->device);
+                cuda_check(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+            }
+            half_bytes = (half_bytes + half_bytes / 4 + (1 << 20) - 1) >> 20 << 20;
+            std::vector<char *> arenas(g->members.size(), nullptr);
+            for (size_t r = 0; r < g->members.size(); ++r) {
+                Comm *m = g->members[r];
+                release_arena(m);
+                use_device(m->device);
+                cuda_check(cudaMalloc((void **)&arenas[r], 2 * half_bytes), "cudaMalloc (arena)");
+            }
+            for (size_t r = 0; r < g->members.size(); ++r) {
+                Comm *m = g->members[r];
+                m->arena = arenas[r], m->half_bytes = half_bytes, m->peer = arenas;
+                for (Comm *o : g->members) enable_peer(m->device, o->device);
+            }
+        }
+
         /// Make every rank's arena at least 2 x half_bytes and map it everywhere. Collective.
         void ensure_arena(Comm *c, size_t half_bytes) {
+            if (c->local) return ensure_arena_local(c, half_bytes);
             if (half_bytes <= c->half_bytes) return;
             DeviceState &d = device_state(c->device);
             use_device(c->device);
@@ -382,14 +407,50 @@ namespace sbb {
             c->p2p = !(e && std::atoi(e) == 0);
             // every rank must take the same decision
             c->p2p = agree_min(c, c->p2p ? 1 : 0) != 0;
-            const char *sg = std::getenv("SBB_P2P_SIGNAL");
-            c->signal = agree_min(c, (sg && std::atoi(sg) == 0) ? 0 : 1) != 0;
         }
         return c;
     }
 
+    std::vector<Comm *> comm_create_local(int nranks, const int *devices) {
+        if (nranks < 1) throw std::runtime_error("invalid number of ranks");
+        LocalGroup *g = new LocalGroup;
+        g->begun.assign(nranks, 0);
+        g->round_ev.resize(nranks);
+        for (int r = 0; r < nranks; ++r) {
+            device_state(devices[r]);
+            Comm *c = new Comm;
+            c->nranks = nranks, c->rank = r, c->device = devices[r];
+            c->local = g, c->p2p = true;
+            g->members.push_back(c);
+        }
+        return g->members;
+    }
+
     void comm_destroy(Comm *c) {
         if (!c) return;
+        if (c->pending) {
+            try {
+                c->pending->finish();
+            } catch (...) {
+            }
+            c->pending = nullptr;
+        }
+        use_device(c->device);
+        for (auto e : c->events) cudaEventDestroy(e);
+        c->events.clear();
+        if (c->local) {
+            LocalGroup *g = c->local;
+            cudaDeviceSynchronize();
+            release_arena(c);
+            for (auto e : g->round_ev[c->rank]) cudaEventDestroy(e);
+            g->round_ev[c->rank].clear();
+            g->members[c->rank] = nullptr;
+            bool last = true;
+            for (Comm *m : g->members) last = last && m == nullptr;
+            if (last) delete g;
+            delete c;
+            return;
+        }
         if (c->nccl) {
             use_device(c->device);
             cudaStreamSynchronize(device_state(c->device).stream);
@@ -404,7 +465,7 @@ namespace sbb {
     }
 
     void comm_check(Comm *c) {
-        if (!c || !c->nccl) return;
+        if (!c || !c->usable()) return;
         if (c->error_host && *(volatile int *)c->error_host != 0) {
             c->poisoned = true;
             throw std::runtime_error("exchange timed out waiting for rank " +
@@ -487,22 +548,11 @@ namespace sbb {
                 blocks.emplace_back(device, p);
                 return p;
             }
-            ~PoolGuard() {
+            void release() {
                 for (auto &b : blocks) pool_free(b.first, b.second);
+                blocks.clear();
             }
-        };
-
-        /// An exception between the first and the last step of an exchange leaves this rank's view
-        /// of the communicator (arena half, sequence numbers) ahead of or behind the other ranks'
-        struct ExchangeGuard {
-            Comm *comm;
-            bool armed = true;
-            explicit ExchangeGuard(Comm *c) : comm(c) {}
-            ~ExchangeGuard() {
-                set_grid_cap(0);
-                set_exchange_sync(nullptr);
-                if (armed && comm) comm->poisoned = true;
-            }
+            ~PoolGuard() { release(); }
         };
 
         struct Resolved {
@@ -513,48 +563,206 @@ namespace sbb {
             size_t bytes = 0;
             bool used = false;
         };
+
+        /// CTAs of the pack kernels of a peer-memory exchange (NVLink, not HBM, bounds them) and of
+        /// the kernels that run beside them on the auxiliary stream; measured in round 1 on 2 and 4
+        /// GPUs (pack 24..296 tried; auxiliary 0 = no limit 3.18 ms, 148 2.69, 222 2.57)
+        int pack_grid() {
+            static int v = -1;
+            if (v < 0) {
+                const char *e = std::getenv("SBB_P2P_PACK_GRID");
+                v = e ? std::atoi(e) : 74;
+            }
+            return v;
+        }
+        int aux_grid_default() {
+            static int v = -1;
+            if (v < 0) {
+                const char *e = std::getenv("SBB_P2P_AUX_GRID");
+                v = e ? std::atoi(e) : 222;
+            }
+            return v;
+        }
+
+        /// At least n events of the communicator's set `which` (0 / 1, alternating per exchange)
+        cudaEvent_t comm_event(Comm *c, int which, int i, int n) {
+            const size_t need = (size_t)2 * n;
+            use_device(c->device);
+            while (c->events.size() < need) {
+                cudaEvent_t e;
+                cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
+                c->events.push_back(e);
+            }
+            // sets are interleaved so that growing the vector keeps the earlier assignments
+            return c->events[(size_t)2 * i + which];
+        }
+        cudaEvent_t local_round_event(LocalGroup *g, int rank, int device, size_t slot) {
+            auto &v = g->round_ev[rank];
+            use_device(device);
+            while (v.size() <= slot) {
+                cudaEvent_t e;
+                cuda_check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event");
+                v.push_back(e);
+            }
+            return v[slot];
+        }
     }
 
-    void execute_copy(const CopyPlan &plan, const CopyArgs &args, int dtype0, int dtype1,
-                      const double *alpha, const std::vector<Buffer> &v0,
-                      const std::vector<Buffer> &v1, Comm *comm,
-                      const std::vector<Buffer> *mask_a, const std::vector<Buffer> *mask_b) {
-        set_exchange_sync(nullptr); // nothing left over from a call that ended with an exception
-        set_grid_cap(0);
-        comm_check(comm);
-        // a rank without work still takes part in the barrier of the peer-memory transport
-        if (plan.ops.empty() && !(comm && comm->nccl && comm->p2p && plan.any_comm)) return;
-        const int es0 = dtype_bytes(dtype0), es1 = dtype_bytes(dtype1);
-        // Element type on the wire: the destination type, so that conversions happen once, before
-        // sending (as the reference does, dist.h:1450-1451) -- except when adding with a type
-        // change, where the scaled source type travels so that the receiver performs exactly the
-        // arithmetic of a local `w += alpha*v` (copy_n.h:216-232)
-        const int wire_dtype = (args.add && dtype0 != dtype1) ? dtype0 : dtype1;
-        const int esw = dtype_bytes(wire_dtype);
-        const int me = plan.rank;
-        if (plan.needs_comm && (!comm || !comm->nccl))
-            throw std::runtime_error("copy needs communication but no communicator was given");
+    struct CopyExec::Impl {
+        std::shared_ptr<const CopyPlan> plan_ptr;
+        CopyArgs args;
+        int dtype0, dtype1;
+        double alpha[2];
+        std::vector<Buffer> v0, v1, mask_a, mask_b;
+        bool has_mask_a = false, has_mask_b = false;
+        Comm *comm;
+        enum State { Created, Begun, Finished, Failed } state = Created;
 
+        // ---- derived in begin() -------------------------------------------------------------------
+        int es0 = 0, es1 = 0, wire_dtype = 0, esw = 0, me = 0, home = -1;
         PoolGuard pool;
+        std::vector<Resolved> s, d;
+        std::set<int> devs;
+        std::vector<const float *> mA, mB;
+        enum Transport { None, Peer, Nccl } transport = None;
+        bool exchange_open = false; ///< between the first and the last step of an exchange on `comm`
+        std::vector<size_t> seg_send, seg_recv;
+        char *sendbuf = nullptr, *recvbuf = nullptr;
+        std::vector<char *> p2p_send_base, p2p_recv_base;
+        bool use_aux = false;
+        int aux_grid = 0, nrounds = 0, evset = 0;
+        unsigned long long seq0 = 0, exchange_id = 0;
+        bool local_done = false, nothing_to_do = false;
+        std::vector<std::vector<int64_t>> rlo, rhi; // NCCL transport: receive windows per (round, peer)
+
+        const CopyPlan &plan() const { return *plan_ptr; }
+        DeviceState &hs() { return device_state(home); }
+        cudaStream_t stream_for(int dev) {
+            return use_aux && dev == home ? hs().aux_stream : device_state(dev).stream;
+        }
+        int round_of(const BoxOp &op) const {
+            const int64_t chunk = std::max<int64_t>(args.chunk_bytes, 1);
+            const int64_t off = (op.kind == BoxOp::Pack ? op.doff : op.soff) * esw;
+            return args.chunk_bytes > 0 ? (int)(off / chunk) : 0;
+        }
+
+        void cross_sync(bool begin_side) {
+            // Several devices in one process: order their streams before and after (the reference's
+            // causalConnectTo, platform.h:371-409)
+            if (devs.size() < 2) return;
+            for (int a : devs) {
+                DeviceState &da = device_state(a);
+                use_device(a);
+                cuda_check(cudaEventRecord(begin_side ? da.ev_a : da.ev_b, da.stream), "cudaEventRecord");
+            }
+            for (int a : devs)
+                for (int b : devs) {
+                    if (a == b) continue;
+                    use_device(a);
+                    cuda_check(cudaStreamWaitEvent(device_state(a).stream,
+                                                   begin_side ? device_state(b).ev_a : device_state(b).ev_b, 0),
+                               "cudaStreamWaitEvent");
+                }
+        }
+
+        void run(const BoxOp &op) {
+            // While an exchange is in flight the kernels on the auxiliary stream (local part, unpack)
+            // run on a reduced grid: they are persistent, and at full width they would hold every
+            // SM until they end, so that the pack kernels of the next round could not start beside them
+            struct CapGuard {
+                int saved;
+                bool on;
+                CapGuard(bool on_, int cap) : saved(grid_cap()), on(on_) {
+                    if (on) set_grid_cap(cap);
+                }
+                ~CapGuard() {
+                    if (on) set_grid_cap(saved);
+                }
+            } guard(use_aux && aux_grid > 0 && op.kind != BoxOp::Pack, aux_grid);
+            const double one[2] = {1, 0}, zero[2] = {0, 0};
+            sbk_box_desc desc = to_desc(op);
+            switch (op.kind) {
+            case BoxOp::Local: {
+                const Resolved &a = s[op.src_comp], &b = d[op.dst_comp];
+                enable_peer(b.device, a.device);
+                use_device(b.device);
+                desc.soff = op.soff, desc.doff = op.doff;
+                permute_copy(desc, a.ptr, dtype0, b.ptr, dtype1, alpha, args.add, b.device,
+                             stream_for(b.device), nullptr, mA[op.dst_comp], mB[op.dst_comp]);
+                break;
+            }
+            case BoxOp::Pack: {
+                const Resolved &a = s[op.src_comp];
+                enable_peer(home, a.device);
+                use_device(home);
+                desc.soff = op.soff, desc.doff = op.doff;
+                // scaled (and normally converted) before it leaves; with the peer-memory transport
+                // the kernel's stores go straight into the receiver's arena over NVLink
+                char *to = transport == Peer ? p2p_send_base[op.peer] : sendbuf + seg_send[op.peer];
+                permute_copy(desc, a.ptr, dtype0, to, wire_dtype, alpha, false, home, hs().stream);
+                break;
+            }
+            case BoxOp::Unpack: {
+                const Resolved &b = d[op.dst_comp];
+                enable_peer(b.device, home);
+                use_device(b.device);
+                desc.soff = op.soff, desc.doff = op.doff;
+                const char *from = transport == Peer ? p2p_recv_base[op.peer] : recvbuf + seg_recv[op.peer];
+                permute_copy(desc, from, wire_dtype, b.ptr, dtype1, one, args.add, b.device,
+                             stream_for(b.device), nullptr, mA[op.dst_comp], mB[op.dst_comp]);
+                break;
+            }
+            case BoxOp::Zero: {
+                const Resolved &b = d[op.dst_comp];
+                use_device(b.device);
+                desc.doff = op.doff;
+                // uncovered destination: only the destination's own mask applies (dist.h:2363-2367)
+                permute_copy(desc, nullptr, dtype1, b.ptr, dtype1, zero, false, b.device,
+                             stream_for(b.device), nullptr, nullptr, mB[op.dst_comp]);
+                break;
+            }
+            }
+        }
+        void run_local_part() {
+            for (const auto &op : plan().ops)
+                if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
+        }
+
+        void resolve_buffers();
+        void begin();
+        void begin_peer();
+        void begin_nccl();
+        void finish();
+        void finish_peer();
+        void finish_nccl();
+        void fail() {
+            state = Failed;
+            set_grid_cap(0);
+            set_exchange_sync(nullptr);
+            if (exchange_open && comm) {
+                comm->poisoned = true;
+                if (comm->pending && comm->pending->impl == this) comm->pending = nullptr;
+            }
+        }
+    };
+
+    void CopyExec::Impl::resolve_buffers() {
         // Which components take part, and how much of every destination is overwritten
-        std::vector<Resolved> s(v0.size()), d(v1.size());
+        s.assign(v0.size(), Resolved()), d.assign(v1.size(), Resolved());
         std::vector<int64_t> written(v1.size(), 0);
-        for (const auto &op : plan.ops) {
+        for (const auto &op : plan().ops) {
             if (op.src_comp >= 0) s[op.src_comp].used = true;
             if (op.dst_comp >= 0) d[op.dst_comp].used = true, written[op.dst_comp] += op.volume();
         }
-
         // Home device: where host buffers are staged and where messages are packed
-        int home = -1;
+        home = -1;
         if (comm) home = comm->device;
         for (size_t c = 0; c < v1.size() && home < 0; ++c)
             if (d[c].used && !v1[c].host) home = v1[c].device;
         for (size_t c = 0; c < v0.size() && home < 0; ++c)
             if (s[c].used && !v0[c].host) home = v0[c].device;
         if (home < 0) home = default_device(comm);
-        DeviceState &hs = device_state(home);
-
-        std::set<int> devs;
+        DeviceState &h = hs();
         devs.insert(home);
         for (size_t c = 0; c < v0.size(); ++c) {
             if (!s[c].used) continue;
@@ -567,8 +775,7 @@ namespace sbb {
                 s[c].staged = pool.alloc(home, s[c].bytes);
                 s[c].ptr = (char *)s[c].staged;
                 use_device(home);
-                cuda_check(cudaMemcpyAsync(s[c].ptr, v0[c].ptr, s[c].bytes, cudaMemcpyHostToDevice,
-                                           hs.stream),
+                cuda_check(cudaMemcpyAsync(s[c].ptr, v0[c].ptr, s[c].bytes, cudaMemcpyHostToDevice, h.stream),
                            "cudaMemcpyAsync H2D");
             } else {
                 s[c].ptr = (char *)v0[c].ptr, s[c].device = v0[c].device;
@@ -576,6 +783,7 @@ namespace sbb {
             }
             devs.insert(s[c].device);
         }
+        const bool masked = has_mask_a || has_mask_b;
         for (size_t c = 0; c < v1.size(); ++c) {
             if (!d[c].used) continue;
             const int64_t vol = volume(args.p1[me * args.ncomp1 + c].size);
@@ -587,10 +795,9 @@ namespace sbb {
                 d[c].staged = pool.alloc(home, d[c].bytes);
                 d[c].ptr = (char *)d[c].staged;
                 // keep what the copy does not overwrite (Copy ops never overlap, see plan.cpp)
-                if (args.add || written[c] < vol || mask_a || mask_b) {
+                if (args.add || written[c] < vol || masked) {
                     use_device(home);
-                    cuda_check(cudaMemcpyAsync(d[c].ptr, v1[c].ptr, d[c].bytes,
-                                               cudaMemcpyHostToDevice, hs.stream),
+                    cuda_check(cudaMemcpyAsync(d[c].ptr, v1[c].ptr, d[c].bytes, cudaMemcpyHostToDevice, h.stream),
                                "cudaMemcpyAsync H2D");
                 }
             } else {
@@ -599,17 +806,16 @@ namespace sbb {
             }
             devs.insert(d[c].device);
         }
-
         // Masks of the destination components (MaskType = float, laid out like the component): host
         // masks are staged next to the component's data
-        std::vector<const float *> mA(v1.size(), nullptr), mB(v1.size(), nullptr);
+        mA.assign(v1.size(), nullptr), mB.assign(v1.size(), nullptr);
         for (int which = 0; which < 2; ++which) {
-            const std::vector<Buffer> *m = which ? mask_b : mask_a;
-            if (!m) continue;
-            if (m->size() != v1.size()) throw std::runtime_error("copy: one mask per component expected");
+            if (!(which ? has_mask_b : has_mask_a)) continue;
+            const std::vector<Buffer> &m = which ? mask_b : mask_a;
+            if (m.size() != v1.size()) throw std::runtime_error("copy: one mask per component expected");
             for (size_t c = 0; c < v1.size(); ++c) {
                 if (!d[c].used) continue;
-                const Buffer &b = (*m)[c];
+                const Buffer &b = m[c];
                 if (!b.ptr) throw std::runtime_error("copy: null mask for a non-empty component");
                 const float *ptr = (const float *)b.ptr;
                 if (b.host) {
@@ -627,419 +833,361 @@ namespace sbb {
                 (which ? mB : mA)[c] = ptr;
             }
         }
-        auto ma = [&](int comp) { return mA[comp]; };
-        auto mb = [&](int comp) { return mB[comp]; };
+    }
 
-        // Several devices in one process: order their streams before and after (the reference's
-        // causalConnectTo, platform.h:371-409)
-        auto cross_sync = [&](bool begin) {
-            if (devs.size() < 2) return;
-            for (int a : devs) {
-                DeviceState &da = device_state(a);
-                use_device(a);
-                cuda_check(cudaEventRecord(begin ? da.ev_a : da.ev_b, da.stream), "cudaEventRecord");
-            }
-            for (int a : devs)
-                for (int b : devs) {
-                    if (a == b) continue;
-                    use_device(a);
-                    cuda_check(cudaStreamWaitEvent(device_state(a).stream,
-                                                   begin ? device_state(b).ev_a : device_state(b).ev_b, 0),
-                               "cudaStreamWaitEvent");
-                }
-        };
+    void CopyExec::Impl::begin() {
+        if (state != Created) throw std::runtime_error("copy request: begun twice");
+        set_exchange_sync(nullptr); // nothing left over from a call that ended with an exception
+        set_grid_cap(0);
+        comm_check(comm);
+        const CopyPlan &pl = plan();
+        const bool peer_capable = comm && comm->usable() && comm->p2p && pl.any_comm;
+        // a rank without work still takes part in the synchronisation of the peer-memory transport
+        if (pl.ops.empty() && !peer_capable) {
+            nothing_to_do = true;
+            state = Begun;
+            return;
+        }
+        es0 = dtype_bytes(dtype0), es1 = dtype_bytes(dtype1);
+        // Element type on the wire: the destination type, so that conversions happen once, before
+        // sending (as the reference does, dist.h:1450-1451) -- except when adding with a type
+        // change, where the scaled source type travels so that the receiver performs exactly the
+        // arithmetic of a local `w += alpha*v` (copy_n.h:216-232)
+        wire_dtype = (args.add && dtype0 != dtype1) ? dtype0 : dtype1;
+        esw = dtype_bytes(wire_dtype);
+        me = pl.rank;
+        if (pl.needs_comm && (!comm || !comm->usable()))
+            throw std::runtime_error("copy needs communication but no communicator was given");
+        // one exchange at a time per communicator: complete the previous one first
+        if (comm && comm->pending && (peer_capable || pl.needs_comm)) comm->pending->finish();
+
+        resolve_buffers();
         cross_sync(true);
 
-        // Peer-memory transport: all ranks take the same decision from plan-wide quantities
-        const bool p2p = comm && comm->nccl && comm->p2p && plan.any_comm;
-        ExchangeGuard exchange_guard(p2p || plan.needs_comm ? comm : nullptr);
-        if (p2p) ensure_arena(comm, (size_t)plan.arena_elems * esw);
-        const bool use_p2p = p2p && comm->p2p; // ensure_arena may have disabled it (collectively)
+        // Transport: all ranks take the same decision from plan-wide quantities
+        if (peer_capable || pl.needs_comm) exchange_open = true;
+        if (peer_capable) ensure_arena(comm, (size_t)pl.arena_elems * esw);
+        if (peer_capable && comm->p2p) // ensure_arena may have disabled it (collectively)
+            transport = Peer;
+        else if (pl.needs_comm)
+            transport = Nccl;
+        if (transport == Nccl && comm->local)
+            throw std::runtime_error("loopback communicators only have the peer-memory transport");
+        if (transport == None) exchange_open = false;
 
-        // Message buffers: one 256-byte aligned segment per peer
-        std::vector<size_t> seg_send(plan.nranks + 1, 0), seg_recv(plan.nranks + 1, 0);
-        char *sendbuf = nullptr, *recvbuf = nullptr;
-        if (plan.needs_comm && !use_p2p) {
-            for (int r = 0; r < plan.nranks; ++r) {
-                seg_send[r + 1] = seg_send[r] + ((size_t)plan.send_elems[r] * esw + 255) / 256 * 256;
-                seg_recv[r + 1] = seg_recv[r] + ((size_t)plan.recv_elems[r] * esw + 255) / 256 * 256;
-            }
-            if (seg_send[plan.nranks]) sendbuf = (char *)pool.alloc(home, seg_send[plan.nranks]);
-            if (seg_recv[plan.nranks]) recvbuf = (char *)pool.alloc(home, seg_recv[plan.nranks]);
-        }
+        if (transport == Peer) begin_peer();
+        else if (transport == Nccl) begin_nccl();
+        else
+            for (const auto &op : pl.ops) run(op);
+        state = Begun;
+    }
 
-        // Optional DMA variant of the peer-memory exchange (SBB_P2P_DMA_MB = message size in MB from
-        // which it is used; default 0 = never): the pack kernels fill a local send buffer at HBM speed
-        // and a copy engine pushes every round's window into the receiver's arena.  Measured on this
-        // pool's B200 pairs it is SLOWER than stores issued by the pack kernels themselves (3.9 ms vs
-        // 2.6 ms for the 2-GPU redistribution of config 3: the copy engine moves ~220 GB/s per
-        // direction, the kernels' stores ~310 GB/s), so it stays off; kept for boxes where the balance
-        // differs.  All ranks take the same decision (max_pair_elems is a property of the exchange).
-        bool dma = false;
-        if (use_p2p) {
-            static long long thr = -1;
-            if (thr < 0) {
-                const char *e = std::getenv("SBB_P2P_DMA_MB");
-                thr = (e ? std::atoll(e) : 0) << 20;
-            }
-            dma = thr > 0 && plan.max_pair_elems * (int64_t)esw >= thr;
-            if (dma) {
-                for (int r = 0; r < plan.nranks; ++r)
-                    seg_send[r + 1] = seg_send[r] + ((size_t)plan.send_elems[r] * esw + 255) / 256 * 256;
-                if (seg_send[plan.nranks]) sendbuf = (char *)pool.alloc(home, seg_send[plan.nranks]);
-            }
-        }
-        std::vector<char *> p2p_send_base(plan.nranks, nullptr), p2p_recv_base(plan.nranks, nullptr);
-        if (use_p2p) {
-            const size_t half = (comm->epoch & 1) * comm->half_bytes;
-            for (int r = 0; r < plan.nranks; ++r) {
-                p2p_send_base[r] = comm->peer[r] + half + (size_t)plan.send_seg_off[r] * esw;
-                p2p_recv_base[r] = comm->arena + half + (size_t)plan.recv_seg_off[r] * esw;
-            }
-            ++comm->epoch;
-        }
-        const double one[2] = {1, 0}, zero[2] = {0, 0};
-        // kernels that write the destination normally go to the destination device's stream; during a
-        // peer-memory exchange those of the home device go to its auxiliary stream so that they run
-        // beside the (NVLink-bound) pack kernels
-        bool use_aux = false;
-        auto stream_for = [&](int dev) {
-            return use_aux && dev == home ? hs.aux_stream : device_state(dev).stream;
-        };
-        // While an exchange is in flight the kernels on the auxiliary stream (local part, unpack) run
-        // on a reduced grid (aux_grid CTAs, 0 = no limit): they are persistent, and at full width
-        // they would hold every SM until they end, so that the pack kernels of the next round could
-        // not start beside them.
-        int aux_grid = 0;
-        auto run = [&](const BoxOp &op) {
-            struct CapGuard {
-                int saved;
-                bool on;
-                CapGuard(bool on_, int cap) : saved(grid_cap()), on(on_) {
-                    if (on) set_grid_cap(cap);
-                }
-                ~CapGuard() {
-                    if (on) set_grid_cap(saved);
-                }
-            } guard(use_aux && aux_grid > 0 && op.kind != BoxOp::Pack, aux_grid);
-            sbk_box_desc desc = to_desc(op);
-            switch (op.kind) {
-            case BoxOp::Local: {
-                const Resolved &a = s[op.src_comp], &b = d[op.dst_comp];
-                enable_peer(b.device, a.device);
-                use_device(b.device);
-                desc.soff = op.soff, desc.doff = op.doff;
-                permute_copy(desc, a.ptr, dtype0, b.ptr, dtype1, alpha, args.add, b.device,
-                             stream_for(b.device), nullptr, ma(op.dst_comp), mb(op.dst_comp));
-                break;
-            }
-            case BoxOp::Pack: {
-                const Resolved &a = s[op.src_comp];
-                enable_peer(home, a.device);
-                use_device(home);
-                desc.soff = op.soff, desc.doff = op.doff;
-                // scaled (and normally converted) before it leaves; with the peer-memory transport
-                // the kernel's stores go straight into the receiver's arena over NVLink
-                char *to = use_p2p && !dma ? p2p_send_base[op.peer] : sendbuf + seg_send[op.peer];
-                permute_copy(desc, a.ptr, dtype0, to, wire_dtype, alpha, false, home, hs.stream);
-                break;
-            }
-            case BoxOp::Unpack: {
-                const Resolved &b = d[op.dst_comp];
-                enable_peer(b.device, home);
-                use_device(b.device);
-                desc.soff = op.soff, desc.doff = op.doff;
-                const char *from = use_p2p ? p2p_recv_base[op.peer] : recvbuf + seg_recv[op.peer];
-                permute_copy(desc, from, wire_dtype, b.ptr, dtype1, one, args.add, b.device,
-                             stream_for(b.device), nullptr, ma(op.dst_comp), mb(op.dst_comp));
-                break;
-            }
-            case BoxOp::Zero: {
-                const Resolved &b = d[op.dst_comp];
-                use_device(b.device);
-                desc.doff = op.doff;
-                // uncovered destination: only the destination's own mask applies (dist.h:2363-2367)
-                permute_copy(desc, nullptr, dtype1, b.ptr, dtype1, zero, false, b.device,
-                             stream_for(b.device), nullptr, nullptr, mb(op.dst_comp));
-                break;
-            }
-            }
-        };
-
-        // ---- exchange, pipelined in rounds ------------------------------------------------------------
-        // A round is a window of `chunk` bytes of every peer's segment: the ops whose wire range
-        // starts inside it.  Round k: pack (compute stream) -> event -> grouped ncclSend/ncclRecv
-        // of that window (communication stream) -> event -> unpack.  All packs are queued first, so
-        // the transfer of round k overlaps the packing of rounds > k and the unpacking of rounds < k;
-        // the local part of a Copy is queued right after the first pack.  Sender and receiver derive
-        // the same rounds because they derive the same wire offsets.
+    // ---- peer-memory exchange --------------------------------------------------------------------
+    // Pack kernels write into the receivers' arenas; the last CTA of a round's last pack kernel
+    // raises this rank's flag at every receiver (processes) or an event is recorded behind it
+    // (loopback).  The arena halves alternate, and every exchange ends with the compute stream
+    // waiting for every rank's last signal, so a sender can only overwrite a half after its previous
+    // readers have finished.  The exchange is cut in rounds (windows of `chunk` bytes
+    // of every segment): round k's unpack kernels (auxiliary stream) overlap the pack kernels of the
+    // later rounds (compute stream); the pack kernels run on a reduced grid because NVLink, not
+    // HBM, bounds them, which leaves SM resources for the kernels on the auxiliary stream.  Queue
+    // order matters (the kernels are persistent): packs of round 0 and their signal first, then the
+    // local part on the auxiliary stream.
+    void CopyExec::Impl::begin_peer() {
+        const CopyPlan &pl = plan();
         const int64_t chunk = std::max<int64_t>(args.chunk_bytes, 1);
-        auto round_of = [&](const BoxOp &op) {
-            const int64_t off = (op.kind == BoxOp::Pack ? op.doff : op.soff) * esw;
-            return args.chunk_bytes > 0 ? (int)(off / chunk) : 0;
-        };
-        if (use_p2p) {
-            // ---- peer-memory exchange --------------------------------------------------------------
-            // pack kernels write into the receivers' arenas and raise this rank's flag there when their
-            // last CTA is done (or, SBB_P2P_SIGNAL=0, one small all-reduce on the communication stream
-            // is the barrier "every rank's stores are done").  The arena halves alternate, and every
-            // call ends with the compute stream waiting for every rank's last signal, so a sender can
-            // only overwrite a half after its previous readers have finished.
-            // The exchange is cut in rounds (windows of `chunk` bytes of every segment): round k's
-            // unpack kernels (auxiliary stream) overlap the pack kernels of the later rounds
-            // (compute stream); the pack kernels run on a reduced grid because NVLink, not HBM,
-            // bounds them, which leaves SM resources for the kernels on the auxiliary stream.
-            // all ranks run the same number of barriers: the round count comes from the largest
-            // message of the whole exchange
-            const int nrounds = args.chunk_bytes > 0
-                                    ? (int)std::max<int64_t>(1, (plan.max_pair_elems * esw + chunk - 1) / chunk)
-                                    : 1;
-            static int pack_grid = -1;
-            if (pack_grid < 0) {
-                const char *e = std::getenv("SBB_P2P_PACK_GRID");
-                pack_grid = e ? std::atoi(e) : 74; // measured best on 2 and 4 GPUs (24..296 tried)
-            }
-            {
-                static int v = -1;
-                if (v < 0) {
-                    const char *e = std::getenv("SBB_P2P_AUX_GRID");
-                    v = e ? std::atoi(e) : 222; // measured on 2 GPUs: 0 (no limit) 3.18 ms, 148 2.69, 222 2.57
-                }
-                // only worth it when there are several rounds of NVLink-bound packs to overlap with
-                aux_grid = (nrounds > 1 && !dma) ? v : 0;
-            }
-            std::vector<cudaEvent_t> &evs = round_events(home, 2 * nrounds);
-            use_device(home);
-            cuda_check(cudaEventRecord(hs.ev_a, hs.stream), "cudaEventRecord");
-            cuda_check(cudaStreamWaitEvent(hs.aux_stream, hs.ev_a, 0), "cudaStreamWaitEvent");
-            use_aux = true;
-            // Queue order matters: the (persistent) kernels of the local part fill every SM, so the pack
-            // kernels of round 0 and their signal are queued first; the local part follows on the
-            // auxiliary stream and runs beside them.
-            const bool sig = comm->signal;
-            const unsigned long long seq0 = comm->seq;
-            if (sig) comm->seq += (unsigned long long)nrounds;
-            bool local_done = args.add;
-            // byte window of every (round, peer) of what this rank sends: [lo, hi)
-            std::vector<std::vector<int64_t>> wlo, whi;
-            if (dma) {
-                wlo.assign(nrounds, std::vector<int64_t>(plan.nranks, -1)), whi = wlo;
-                for (const auto &op : plan.ops) {
-                    if (op.kind != BoxOp::Pack) continue;
-                    const int k = round_of(op);
-                    const int64_t b0 = op.doff * esw, b1 = b0 + op.volume() * esw;
-                    auto &lo = wlo[k][op.peer];
-                    auto &hi = whi[k][op.peer];
-                    lo = lo < 0 ? b0 : std::min(lo, b0);
-                    hi = std::max(hi, b1);
-                }
-            }
-            static int fuse_signal = -1;
-            if (fuse_signal < 0) {
-                const char *e = std::getenv("SBB_P2P_FUSED_SIGNAL");
-                fuse_signal = e ? std::atoi(e) : 1;
-            }
-            for (int k = 0; k < nrounds; ++k) {
-                set_grid_cap(dma ? 0 : pack_grid);
-                // the signal of the round rides on its last pack kernel (raised by the last CTA to finish)
-                const BoxOp *last_pack = nullptr;
-                for (const auto &op : plan.ops)
-                    if (op.kind == BoxOp::Pack && round_of(op) == k) last_pack = &op;
-                ExchangeSync xs;
+        p2p_send_base.assign(pl.nranks, nullptr), p2p_recv_base.assign(pl.nranks, nullptr);
+        const size_t half = (comm->epoch & 1) * comm->half_bytes;
+        for (int r = 0; r < pl.nranks; ++r) {
+            p2p_send_base[r] = comm->peer[r] + half + (size_t)pl.send_seg_off[r] * esw;
+            p2p_recv_base[r] = comm->arena + half + (size_t)pl.recv_seg_off[r] * esw;
+        }
+        exchange_id = comm->epoch;
+        evset = (int)(comm->epoch & 1);
+        ++comm->epoch;
+        // all ranks run the same number of rounds: it comes from the largest message of the exchange
+        nrounds = args.chunk_bytes > 0
+                      ? (int)std::max<int64_t>(1, (pl.max_pair_elems * esw + chunk - 1) / chunk)
+                      : 1;
+        // only worth it when there are several rounds of NVLink-bound packs to overlap with
+        aux_grid = nrounds > 1 ? aux_grid_default() : 0;
+        DeviceState &h = hs();
+        use_device(home);
+        cuda_check(cudaEventRecord(h.ev_a, h.stream), "cudaEventRecord");
+        cuda_check(cudaStreamWaitEvent(h.aux_stream, h.ev_a, 0), "cudaStreamWaitEvent");
+        use_aux = true;
+        const bool flags = comm->local == nullptr;
+        seq0 = comm->seq;
+        if (flags) comm->seq += (unsigned long long)nrounds;
+        local_done = args.add; // additions keep plan order: everything after the last wait
+        for (int k = 0; k < nrounds; ++k) {
+            set_grid_cap(pack_grid());
+            const BoxOp *last_pack = nullptr;
+            for (const auto &op : pl.ops)
+                if (op.kind == BoxOp::Pack && round_of(op) == k) last_pack = &op;
+            ExchangeSync xs;
+            if (flags) {
                 xs.peer_flags = comm->peer_flags, xs.sig_seq = seq0 + k + 1;
                 xs.done = (unsigned *)comm->flag + 32, xs.nranks = comm->nranks, xs.me = comm->rank;
-                bool signalled = false;
-                for (const auto &op : plan.ops)
-                    if (op.kind == BoxOp::Pack && round_of(op) == k) {
-                        const bool fuse = sig && !dma && fuse_signal && &op == last_pack;
-                        if (fuse) set_exchange_sync(&xs);
-                        run(op);
-                        if (fuse) signalled = !exchange_sync_pending();
-                    }
-                set_grid_cap(0);
-                use_device(home);
-                if (dma) {
-                    // push this round's windows with the copy engines, then signal / barrier behind them
-                    cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
-                    cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
-                    for (int r = 0; r < plan.nranks; ++r)
-                        if (wlo[k][r] >= 0)
-                            cuda_check(cudaMemcpyAsync(p2p_send_base[r] + wlo[k][r],
-                                                       sendbuf + seg_send[r] + wlo[k][r],
-                                                       (size_t)(whi[k][r] - wlo[k][r]),
-                                                       cudaMemcpyDeviceToDevice, hs.comm_stream),
-                                       "cudaMemcpyAsync (peer)");
-                    if (sig) {
-                        launch_signal(comm->peer_flags, comm->rank, comm->nranks, seq0 + k + 1,
-                                      hs.comm_stream);
-                    } else {
-                        nccl_check(nccl().AllReduce(comm->flag, comm->flag + 8, 1, kNcclInt32, kNcclSum,
-                                                    comm->nccl, hs.comm_stream),
-                                   "ncclAllReduce (barrier)");
-                    }
-                    cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
-                } else if (sig) {
-                    // my stores of this round are complete (stream order): tell every rank
-                    if (!signalled)
-                        launch_signal(comm->peer_flags, comm->rank, comm->nranks, seq0 + k + 1, hs.stream);
-                    // the wait kernel of this round may only become resident once my own packs are
-                    // done: queued without this dependency it would sit on an SM through whatever
-                    // long kernel precedes the pack on the compute stream (a contraction whose grid
-                    // is an exact number of waves then needs one wave more)
-                    cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
-                } else {
-                    cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
-                    cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
-                    nccl_check(nccl().AllReduce(comm->flag, comm->flag + 8, 1, kNcclInt32, kNcclSum,
-                                                comm->nccl, hs.comm_stream),
-                               "ncclAllReduce (barrier)");
-                    cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
-                }
-                if (!local_done) {
-                    for (const auto &op : plan.ops)
-                        if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
-                    local_done = true;
-                }
             }
-            auto wait_round = [&](int k) {
-                if (sig) {
-                    // every rank's stores of round k have landed in my arena once all flags reached
-                    // seq.  The (one-warp) wait kernel spins on the communication stream, beside the
-                    // local part, so that the unpack kernels only wait for an event that is normally
-                    // already complete when the auxiliary stream gets there.
-                    use_device(home);
-                    if (!dma) cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
-                    launch_wait(comm->flags, comm->nranks, seq0 + k + 1, hs.comm_stream,
-                                wait_timeout_ns(), comm->error_dev);
-                    cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
+            bool signalled = false;
+            for (const auto &op : pl.ops)
+                if (op.kind == BoxOp::Pack && round_of(op) == k) {
+                    const bool fuse = flags && &op == last_pack;
+                    if (fuse) set_exchange_sync(&xs);
+                    run(op);
+                    if (fuse) signalled = !exchange_sync_pending();
                 }
-                for (int a : devs) {
-                    use_device(a);
-                    cuda_check(cudaStreamWaitEvent(stream_for(a), evs[2 * k + 1], 0), "cudaStreamWaitEvent");
-                }
-            };
-            if (args.add) {
-                for (int k = 0; k < nrounds; ++k) wait_round(k);
-                for (const auto &op : plan.ops)
-                    if (op.kind != BoxOp::Pack) run(op);
-            } else {
-                for (int k = 0; k < nrounds; ++k) {
-                    wait_round(k);
-                    for (const auto &op : plan.ops)
-                        if (op.kind == BoxOp::Unpack && round_of(op) == k) run(op);
-                }
-            }
-            // the compute stream continues after everything of this call: every rank has then seen
-            // every other rank's last signal of this call, which is what makes the alternation of the
-            // arena halves safe (a rank packs call e+1 only after all ranks finished unpacking call e-1)
-            use_device(home);
-            cuda_check(cudaEventRecord(hs.ev_c, hs.aux_stream), "cudaEventRecord");
-            cuda_check(cudaStreamWaitEvent(hs.stream, hs.ev_c, 0), "cudaStreamWaitEvent");
-            // (with DMA also: the send buffer returns to the pool only after the last transfer)
-            cuda_check(cudaStreamWaitEvent(hs.stream, evs[2 * nrounds - 1], 0), "cudaStreamWaitEvent");
-            use_aux = false;
-        } else if (plan.needs_comm) {
-            // leave room for NCCL's kernels next to ours (SBB_COMM_GRID: CTAs of the copy kernels
-            // while an exchange is in flight; 0 = no limit)
-            static int comm_grid = -1;
-            if (comm_grid < 0) {
-                const char *e = std::getenv("SBB_COMM_GRID");
-                comm_grid = e ? std::atoi(e) : 0;
-            }
-            set_grid_cap(comm_grid);
-            int nrounds = 0;
-            for (const auto &op : plan.ops)
-                if (op.kind == BoxOp::Pack || op.kind == BoxOp::Unpack)
-                    nrounds = std::max(nrounds, round_of(op) + 1);
-            // byte window of every (round, peer): [lo, hi)
-            std::vector<std::vector<int64_t>> slo(nrounds, std::vector<int64_t>(plan.nranks, -1)),
-                shi = slo, rlo = slo, rhi = slo;
-            for (const auto &op : plan.ops) {
-                if (op.kind != BoxOp::Pack && op.kind != BoxOp::Unpack) continue;
-                const int k = round_of(op);
-                const bool snd = op.kind == BoxOp::Pack;
-                const int64_t b0 = (snd ? op.doff : op.soff) * esw, b1 = b0 + op.volume() * esw;
-                auto &lo = (snd ? slo : rlo)[k][op.peer];
-                auto &hi = (snd ? shi : rhi)[k][op.peer];
-                lo = lo < 0 ? b0 : std::min(lo, b0);
-                hi = std::max(hi, b1);
-            }
-            std::vector<cudaEvent_t> &evs = round_events(home, 2 * nrounds);
-            NcclApi &n = nccl();
-            bool local_done = false;
-            for (int k = 0; k < nrounds; ++k) {
-                for (const auto &op : plan.ops)
-                    if (op.kind == BoxOp::Pack && round_of(op) == k) run(op);
-                use_device(home);
-                cuda_check(cudaEventRecord(evs[2 * k], hs.stream), "cudaEventRecord");
-                cuda_check(cudaStreamWaitEvent(hs.comm_stream, evs[2 * k], 0), "cudaStreamWaitEvent");
-                nccl_check(n.GroupStart(), "ncclGroupStart");
-                for (int r = 0; r < plan.nranks; ++r) {
-                    if (slo[k][r] >= 0)
-                        nccl_check(n.Send(sendbuf + seg_send[r] + slo[k][r],
-                                          (size_t)(shi[k][r] - slo[k][r]), kNcclChar, r, comm->nccl,
-                                          hs.comm_stream),
-                                   "ncclSend");
-                    if (rlo[k][r] >= 0)
-                        nccl_check(n.Recv(recvbuf + seg_recv[r] + rlo[k][r],
-                                          (size_t)(rhi[k][r] - rlo[k][r]), kNcclChar, r, comm->nccl,
-                                          hs.comm_stream),
-                                   "ncclRecv");
-                }
-                nccl_check(n.GroupEnd(), "ncclGroupEnd");
-                cuda_check(cudaEventRecord(evs[2 * k + 1], hs.comm_stream), "cudaEventRecord");
-                if (!args.add && !local_done) {
-                    // the local part overlaps the transfers
-                    for (const auto &op : plan.ops)
-                        if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
-                    local_done = true;
-                }
-            }
-            auto wait_round = [&](int k) {
-                for (int a : devs) {
-                    use_device(a);
-                    cuda_check(cudaStreamWaitEvent(device_state(a).stream, evs[2 * k + 1], 0),
-                               "cudaStreamWaitEvent");
-                }
-            };
-            if (args.add) {
-                // additions are applied in plan order (ascending source part) so that the result
-                // does not depend on which contributions were remote
-                for (int k = 0; k < nrounds; ++k) wait_round(k);
-                for (const auto &op : plan.ops)
-                    if (op.kind != BoxOp::Pack) run(op);
-            } else {
-                if (!local_done)
-                    for (const auto &op : plan.ops)
-                        if (op.kind == BoxOp::Local || op.kind == BoxOp::Zero) run(op);
-                for (int k = 0; k < nrounds; ++k) {
-                    wait_round(k);
-                    for (const auto &op : plan.ops)
-                        if (op.kind == BoxOp::Unpack && round_of(op) == k) run(op);
-                }
-            }
             set_grid_cap(0);
-        } else {
-            for (const auto &op : plan.ops) run(op);
+            use_device(home);
+            if (flags) {
+                // my stores of this round are complete (stream order): tell every rank
+                if (!signalled)
+                    launch_signal(comm->peer_flags, comm->rank, comm->nranks, seq0 + k + 1, h.stream);
+                // the wait kernel of this round may only become resident once my own packs are done:
+                // queued without this dependency it would sit on an SM through whatever long kernel
+                // precedes the pack on the compute stream (a contraction whose grid is an exact number
+                // of waves then needs one wave more)
+                cuda_check(cudaEventRecord(comm_event(comm, evset, 2 * k, 2 * nrounds), h.stream),
+                           "cudaEventRecord");
+            } else {
+                cuda_check(cudaEventRecord(local_round_event(comm->local, comm->rank, home,
+                                                             (size_t)2 * k + evset),
+                                           h.stream),
+                           "cudaEventRecord");
+            }
+            if (!local_done) {
+                run_local_part();
+                local_done = true;
+            }
         }
+        if (comm->local) comm->local->begun[comm->rank] = exchange_id + 1;
+    }
 
+    void CopyExec::Impl::finish_peer() {
+        const CopyPlan &pl = plan();
+        DeviceState &h = hs();
+        const bool flags = comm->local == nullptr;
+        if (!flags) {
+            for (int q = 0; q < comm->nranks; ++q)
+                if (comm->local->begun[q] < exchange_id + 1)
+                    throw std::runtime_error("loopback communicators: every rank must begin a copy "
+                                             "(with a Request) before any rank completes it");
+        }
+        auto wait_round = [&](int k) {
+            use_device(home);
+            cudaEvent_t arrived = comm_event(comm, evset, 2 * k + 1, 2 * nrounds);
+            if (flags) {
+                // every rank's stores of round k have landed in my arena once all flags reached the
+                // sequence number.  The one-warp wait kernel spins on the communication stream
+                cuda_check(cudaStreamWaitEvent(h.comm_stream, comm_event(comm, evset, 2 * k, 2 * nrounds), 0),
+                           "cudaStreamWaitEvent");
+                launch_wait(comm->flags, comm->nranks, seq0 + k + 1, h.comm_stream, wait_timeout_ns(),
+                            comm->error_dev);
+            } else {
+                for (int q = 0; q < comm->nranks; ++q)
+                    cuda_check(cudaStreamWaitEvent(h.comm_stream,
+                                                   local_round_event(comm->local, q, comm->local->members[q]->device,
+                                                                     (size_t)2 * k + evset),
+                                                   0),
+                               "cudaStreamWaitEvent");
+            }
+            cuda_check(cudaEventRecord(arrived, h.comm_stream), "cudaEventRecord");
+            for (int a : devs) {
+                use_device(a);
+                cuda_check(cudaStreamWaitEvent(stream_for(a), arrived, 0), "cudaStreamWaitEvent");
+            }
+        };
+        if (args.add) {
+            for (int k = 0; k < nrounds; ++k) wait_round(k);
+            for (const auto &op : pl.ops)
+                if (op.kind != BoxOp::Pack) run(op);
+        } else {
+            for (int k = 0; k < nrounds; ++k) {
+                wait_round(k);
+                for (const auto &op : pl.ops)
+                    if (op.kind == BoxOp::Unpack && round_of(op) == k) run(op);
+            }
+        }
+        // the compute stream continues after everything of this call: every rank has then seen every
+        // other rank's last signal of this call, which is what makes the alternation of the arena
+        // halves safe (a rank packs call e+1 only after all ranks finished unpacking call e-1)
+        use_device(home);
+        cuda_check(cudaEventRecord(h.ev_c, h.aux_stream), "cudaEventRecord");
+        cuda_check(cudaStreamWaitEvent(h.stream, h.ev_c, 0), "cudaStreamWaitEvent");
+        cuda_check(cudaStreamWaitEvent(h.stream, comm_event(comm, evset, 2 * nrounds - 1, 2 * nrounds), 0),
+                   "cudaStreamWaitEvent");
+        use_aux = false;
+    }
+
+    // ---- NCCL transport (SBB_P2P=0, or when the arenas cannot be mapped) ----------------------------
+    // Round k: pack (compute stream) -> event -> grouped ncclSend/ncclRecv of that window
+    // (communication stream) -> event -> unpack.  All packs are queued first, so the transfer of
+    // round k overlaps the packing of rounds > k and the unpacking of rounds < k; the local part of
+    // a Copy is queued right after the first pack.
+    void CopyExec::Impl::begin_nccl() {
+        const CopyPlan &pl = plan();
+        DeviceState &h = hs();
+        seg_send.assign(pl.nranks + 1, 0), seg_recv.assign(pl.nranks + 1, 0);
+        for (int r = 0; r < pl.nranks; ++r) {
+            seg_send[r + 1] = seg_send[r] + ((size_t)pl.send_elems[r] * esw + 255) / 256 * 256;
+            seg_recv[r + 1] = seg_recv[r] + ((size_t)pl.recv_elems[r] * esw + 255) / 256 * 256;
+        }
+        if (seg_send[pl.nranks]) sendbuf = (char *)pool.alloc(home, seg_send[pl.nranks]);
+        if (seg_recv[pl.nranks]) recvbuf = (char *)pool.alloc(home, seg_recv[pl.nranks]);
+        evset = (int)(comm->epoch & 1);
+        ++comm->epoch;
+        nrounds = 0;
+        for (const auto &op : pl.ops)
+            if (op.kind == BoxOp::Pack || op.kind == BoxOp::Unpack) nrounds = std::max(nrounds, round_of(op) + 1);
+        // byte window of every (round, peer): [lo, hi)
+        std::vector<std::vector<int64_t>> slo(nrounds, std::vector<int64_t>(pl.nranks, -1)), shi = slo;
+        rlo = slo, rhi = slo;
+        for (const auto &op : pl.ops) {
+            if (op.kind != BoxOp::Pack && op.kind != BoxOp::Unpack) continue;
+            const int k = round_of(op);
+            const bool snd = op.kind == BoxOp::Pack;
+            const int64_t b0 = (snd ? op.doff : op.soff) * esw, b1 = b0 + op.volume() * esw;
+            auto &lo = (snd ? slo : rlo)[k][op.peer];
+            auto &hi = (snd ? shi : rhi)[k][op.peer];
+            lo = lo < 0 ? b0 : std::min(lo, b0);
+            hi = std::max(hi, b1);
+        }
+        NcclApi &n = nccl();
+        local_done = args.add;
+        for (int k = 0; k < nrounds; ++k) {
+            for (const auto &op : pl.ops)
+                if (op.kind == BoxOp::Pack && round_of(op) == k) run(op);
+            use_device(home);
+            cudaEvent_t packed = comm_event(comm, evset, 2 * k, 2 * nrounds),
+                        arrived = comm_event(comm, evset, 2 * k + 1, 2 * nrounds);
+            cuda_check(cudaEventRecord(packed, h.stream), "cudaEventRecord");
+            cuda_check(cudaStreamWaitEvent(h.comm_stream, packed, 0), "cudaStreamWaitEvent");
+            nccl_check(n.GroupStart(), "ncclGroupStart");
+            for (int r = 0; r < pl.nranks; ++r) {
+                if (slo[k][r] >= 0)
+                    nccl_check(n.Send(sendbuf + seg_send[r] + slo[k][r], (size_t)(shi[k][r] - slo[k][r]),
+                                      kNcclChar, r, comm->nccl, h.comm_stream),
+                               "ncclSend");
+                if (rlo[k][r] >= 0)
+                    nccl_check(n.Recv(recvbuf + seg_recv[r] + rlo[k][r], (size_t)(rhi[k][r] - rlo[k][r]),
+                                      kNcclChar, r, comm->nccl, h.comm_stream),
+                               "ncclRecv");
+            }
+            nccl_check(n.GroupEnd(), "ncclGroupEnd");
+            cuda_check(cudaEventRecord(arrived, h.comm_stream), "cudaEventRecord");
+            if (!local_done) { // the local part overlaps the transfers
+                run_local_part();
+                local_done = true;
+            }
+        }
+    }
+
+    void CopyExec::Impl::finish_nccl() {
+        const CopyPlan &pl = plan();
+        auto wait_round = [&](int k) {
+            for (int a : devs) {
+                use_device(a);
+                cuda_check(cudaStreamWaitEvent(device_state(a).stream,
+                                               comm_event(comm, evset, 2 * k + 1, 2 * nrounds), 0),
+                           "cudaStreamWaitEvent");
+            }
+        };
+        if (args.add) {
+            // additions are applied in plan order (ascending source part) so that the result does not
+            // depend on which contributions were remote
+            for (int k = 0; k < nrounds; ++k) wait_round(k);
+            for (const auto &op : pl.ops)
+                if (op.kind != BoxOp::Pack) run(op);
+        } else {
+            if (!local_done) run_local_part();
+            for (int k = 0; k < nrounds; ++k) {
+                wait_round(k);
+                for (const auto &op : pl.ops)
+                    if (op.kind == BoxOp::Unpack && round_of(op) == k) run(op);
+            }
+        }
+    }
+
+    void CopyExec::Impl::finish() {
+        if (state == Finished) return;
+        if (state != Begun) throw std::runtime_error("copy request: not begun (or failed)");
+        if (nothing_to_do) {
+            state = Finished;
+            return;
+        }
+        set_exchange_sync(nullptr);
+        set_grid_cap(0);
+        if (transport == Peer) finish_peer();
+        else if (transport == Nccl) finish_nccl();
         cross_sync(false);
-
-        // Host destinations are complete when the call returns
+        // Host destinations are complete when the request is
         bool host_out = false;
         for (size_t c = 0; c < v1.size(); ++c)
             if (d[c].used && d[c].host) {
                 use_device(home);
-                cuda_check(cudaMemcpyAsync(d[c].host, d[c].ptr, d[c].bytes, cudaMemcpyDeviceToHost,
-                                           hs.stream),
+                cuda_check(cudaMemcpyAsync(d[c].host, d[c].ptr, d[c].bytes, cudaMemcpyDeviceToHost, hs().stream),
                            "cudaMemcpyAsync D2H");
                 host_out = true;
             }
         if (host_out) {
             use_device(home);
-            cuda_check(cudaStreamSynchronize(hs.stream), "cudaStreamSynchronize");
+            cuda_check(cudaStreamSynchronize(hs().stream), "cudaStreamSynchronize");
         }
-        exchange_guard.armed = false;
+        pool.release();
+        if (exchange_open) {
+            exchange_open = false;
+            if (comm->pending && comm->pending->impl == this) comm->pending = nullptr;
+        }
+        state = Finished;
+    }
+
+    CopyExec::CopyExec(std::shared_ptr<const CopyPlan> plan, const CopyArgs &args, int dtype0, int dtype1,
+                       const double *alpha, std::vector<Buffer> v0, std::vector<Buffer> v1, Comm *comm,
+                       const std::vector<Buffer> *mask_a, const std::vector<Buffer> *mask_b)
+        : impl(new Impl) {
+        impl->plan_ptr = std::move(plan), impl->args = args, impl->dtype0 = dtype0, impl->dtype1 = dtype1;
+        impl->alpha[0] = alpha[0], impl->alpha[1] = alpha[1];
+        impl->v0 = std::move(v0), impl->v1 = std::move(v1), impl->comm = comm;
+        if (mask_a) impl->mask_a = *mask_a, impl->has_mask_a = true;
+        if (mask_b) impl->mask_b = *mask_b, impl->has_mask_b = true;
+    }
+
+    CopyExec::~CopyExec() {
+        // a request dropped between begin and finish leaves the ranks out of step
+        if (impl->state == Impl::Begun && impl->exchange_open) impl->fail();
+        delete impl;
+    }
+
+    void CopyExec::begin() {
+        try {
+            impl->begin();
+            if (impl->exchange_open) impl->comm->pending = this;
+        } catch (...) {
+            impl->fail();
+            throw;
+        }
+    }
+
+    void CopyExec::finish() {
+        try {
+            impl->finish();
+        } catch (...) {
+            impl->fail();
+            throw;
+        }
+    }
+
+    void CopyExec::adopt(int device, void *block) { impl->pool.blocks.emplace_back(device, block); }
+
+    void execute_copy(const CopyPlan &plan, const CopyArgs &args, int dtype0, int dtype1,
+                      const double *alpha, const std::vector<Buffer> &v0, const std::vector<Buffer> &v1,
+                      Comm *comm, const std::vector<Buffer> *mask_a, const std::vector<Buffer> *mask_b) {
+        // (the plan outlives the call: wrap it without taking ownership)
+        CopyExec e(std::shared_ptr<const CopyPlan>(std::shared_ptr<const CopyPlan>(), &plan), args, dtype0,
+                   dtype1, alpha, v0, v1, comm, mask_a, mask_b);
+        e.begin();
+        e.finish();
     }
 
 } // namespace sbb

@@ -6,6 +6,7 @@
 #pragma once
 #include "kernels.hpp"
 #include "plan.hpp"
+#include <memory>
 #include <set>
 #include <vector>
 
@@ -31,22 +32,40 @@ namespace sbb {
     void pool_free(int device, void *p);
     void pool_clear();
 
+    class CopyExec;
+    struct Comm;
+
+    /// Several ranks living in ONE process ("loopback" communicators, sbb_comm_create_local): the
+    /// same exchange as between processes -- pack kernels store into the receiver's arena, unpack
+    /// kernels read it -- with plain device pointers instead of IPC mappings and CUDA events instead
+    /// of flags in peer memory (a kernel that spins on a flag must never wait for a kernel of the
+    /// same process that may not have been launched yet).  This is how the cross-rank path is
+    /// exercised on a box with fewer GPUs than ranks; the ranks are driven by one host thread in
+    /// phases: every rank begins the copy (Request), then every rank completes it.
+    struct LocalGroup {
+        std::vector<Comm *> members;
+        std::vector<unsigned long long> begun; ///< exchanges begun by every rank
+        /// [rank][slot]: recorded on the rank's compute stream behind the pack kernels of a round
+        std::vector<std::vector<cudaEvent_t>> round_ev;
+    };
+
     struct Comm {
-        void *nccl = nullptr; ///< ncclComm_t
+        void *nccl = nullptr; ///< ncclComm_t (ranks in different processes)
+        LocalGroup *local = nullptr; ///< ranks in this process (shared by the members)
         int nranks = 1, rank = 0, device = 0;
         // Peer-memory transport: every rank owns a receive arena (two halves, used alternately) that
-        // all other ranks map with CUDA IPC; pack kernels store straight into the receiver's arena
-        // over NVLink and one small NCCL all-reduce per exchange is the barrier.
+        // all other ranks can store into (CUDA IPC mappings between processes); pack kernels write
+        // straight into the receiver's arena over NVLink.
         bool p2p = false;          ///< transport usable (decided collectively at creation)
         char *arena = nullptr;     ///< my arena
         size_t half_bytes = 0;     ///< size of one half
         std::vector<char *> peer;  ///< every rank's arena as mapped here (peer[rank] == arena)
-        unsigned long long epoch = 0;
-        int *flag = nullptr;       ///< device scratch for the barrier / handle exchange
-        // Flag-based signalling (replaces the NCCL all-reduce barrier on the data path): every
-        // arena ends with one 64-bit slot per rank; a sender raises its slot in every receiver's
-        // arena to the sequence number of the round once its pack kernels are done.
-        bool signal = true;                      ///< SBB_P2P_SIGNAL=0 selects the NCCL barrier instead
+        unsigned long long epoch = 0; ///< exchanges begun (selects the arena half)
+        int *flag = nullptr;       ///< device scratch: collective yes/no decisions, handle exchange, CTA counter
+        // Signalling between processes: every arena ends with one 64-bit slot per rank; a sender
+        // raises its slot in every receiver's arena to the sequence number of the round once its
+        // pack kernels are done (the last CTA of the last pack kernel does it), receivers spin on
+        // their own slots with a one-warp kernel.
         unsigned long long seq = 0;              ///< rounds signalled so far (all ranks agree)
         unsigned long long *flags = nullptr;     ///< my slots (inside my arena allocation)
         unsigned long long **peer_flags = nullptr; ///< device array: every rank's slots as mapped here
@@ -55,6 +74,11 @@ namespace sbb {
         // exchange poisons the communicator, because the ranks no longer agree on epoch / seq.
         int *error_host = nullptr, *error_dev = nullptr;
         bool poisoned = false;
+        /// The exchange that has been begun and not completed (at most one per communicator: the
+        /// next one completes it first, which keeps the alternation of the arena halves safe)
+        CopyExec *pending = nullptr;
+        std::vector<cudaEvent_t> events; ///< per-exchange events (two sets, alternating like the arena halves)
+        bool usable() const { return nccl != nullptr || local != nullptr; }
     };
 
     /// Throws when the communicator is poisoned or one of its wait kernels timed out
@@ -62,6 +86,8 @@ namespace sbb {
 
     void nccl_unique_id(void *id128);
     Comm *comm_create(const void *id128, int nranks, int rank, int device);
+    /// `nranks` loopback communicators of one group; rank r works on devices[r]
+    std::vector<Comm *> comm_create_local(int nranks, const int *devices);
     void comm_destroy(Comm *c);
 
     /// A component buffer as given by the caller
@@ -71,6 +97,29 @@ namespace sbb {
         int device = 0;
     };
 
+    /// A copy in two steps (the reference's Request, dist.h:54-61): begin() queues everything that
+    /// does not depend on other ranks -- staging of host components, the pack kernels with their
+    /// signal, the local part -- and finish() the rest: waiting for the other ranks' data, the
+    /// unpack kernels, the copy-back of host destinations (with the only host synchronisation).
+    class CopyExec {
+    public:
+        CopyExec(std::shared_ptr<const CopyPlan> plan, const CopyArgs &args, int dtype0, int dtype1,
+                 const double *alpha, std::vector<Buffer> v0, std::vector<Buffer> v1, Comm *comm,
+                 const std::vector<Buffer> *mask_a = nullptr, const std::vector<Buffer> *mask_b = nullptr);
+        ~CopyExec();
+        CopyExec(const CopyExec &) = delete;
+        CopyExec &operator=(const CopyExec &) = delete;
+        void begin();
+        void finish();
+        /// A pool block that must live until the copy is complete (e.g. the carried mask)
+        void adopt(int device, void *block);
+        struct Impl;
+
+    private:
+        Impl *impl;
+    };
+
+    /// begin() + finish()
     void execute_copy(const CopyPlan &plan, const CopyArgs &args, int dtype0, int dtype1,
                       const double *alpha, const std::vector<Buffer> &v0,
                       const std::vector<Buffer> &v1, Comm *comm,
