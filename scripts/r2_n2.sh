@@ -2,7 +2,7 @@
 # Round 2, 2 GPUs: correctness of the cross-rank path, bench with result checks, peer-store probe.
 N=${N:-2}
 mkdir -p gpurun_out
-scripts/with_timeout.sh 200 env SBB_CHUNK_BYTES=256 OMP_NUM_THREADS=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 tests/dist_check.py --backend nccl --cases 20 > gpurun_out/r2_dist_check_n$N.log 2>&1; echo "dist rc=$?"; grep -E "DIST_CHECK|differs|failures" gpurun_out/r2_dist_check_n$N.log | tail -5
+scripts/with_timeout.sh 200 env SBB_CHUNK_BYTES=256 OMP_NUM_THREADS=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 tests/dist_check.py --backend nccl --cases 20 --stress 1000 > gpurun_out/r2_dist_check_n$N.log 2>&1; echo "dist rc=$?"; grep -E "DIST_CHECK|differs|failures|stress" gpurun_out/r2_dist_check_n$N.log | tail -5
 scripts/with_timeout.sh 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err; echo "bench rc=$?"
 tail -1 gpurun_out/r2_bench_n$N.json | python -c "
 import sys,json

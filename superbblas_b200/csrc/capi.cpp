@@ -270,11 +270,20 @@ namespace {
                                                           buffers((const void *const *)v1, ctx1, ncomponents1), c));
         // Masked copy (reference: tensor.h:1022-1027, dist.h:944-970, :1240-1243): an element moves
         // iff the source mask at its origin and the destination mask at its target are nonzero.
-        // Step 1 carries mask0 to the destination layout with the copy engine itself (a float copy
-        // with the same geometry, exchange included); step 2 is the data copy with the two masks as
-        // a predicate on every destination store.
+        // Purely local copies apply both masks in ONE pass: the source's mask is read with the source
+        // elements (permute_kernel, ma_src).  When parts of the copy are remote, step 1 carries mask0
+        // to the destination layout with the copy engine itself (a float copy with the same
+        // geometry, exchange included) and step 2 is the data copy with the two masks as a predicate
+        // on every destination store.
         std::vector<Buffer> m0b, m1b, tmp;
         if (has_m1) m1b = buffers((const void *const *)mask1, ctx1, ncomponents1);
+        if (has_m0 && !a.alpha_is_zero && !plan->any_comm) {
+            m0b = buffers((const void *const *)mask0, ctx0, ncomponents0);
+            return std::unique_ptr<CopyExec>(new CopyExec(plan, a, dtype0, dtype1, alpha,
+                                                          buffers(v0, ctx0, ncomponents0),
+                                                          buffers((const void *const *)v1, ctx1, ncomponents1), c,
+                                                          nullptr, has_m1 ? &m1b : nullptr, &m0b));
+        }
         struct Blocks {
             std::vector<Buffer> *v;
             bool armed = true;

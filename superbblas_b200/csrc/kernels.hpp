@@ -35,11 +35,12 @@ namespace sbb {
     /// dst (+)= Q(alpha*src) over a strided box. The current device must be `device`.
     /// If `describe` is given nothing is launched and the chosen variant is described instead.
     /// mask_a / mask_b (optional, MaskType = float, laid out exactly like dst): an element of dst
-    /// is written only where every given mask is nonzero.
+    /// is written only where every given mask is nonzero.  mask_src (instead of mask_a): the
+    /// source's mask, laid out exactly like src, applied in the same pass.
     void permute_copy(const sbk_box_desc &box, const void *src, int dtype_src, void *dst,
                       int dtype_dst, const double *alpha, bool add, int device, cudaStream_t stream,
                       std::string *describe = nullptr, const float *mask_a = nullptr,
-                      const float *mask_b = nullptr);
+                      const float *mask_b = nullptr, const float *mask_src = nullptr);
 
     /// Peer-memory signalling of an exchange round: `launch_signal` (queued behind the pack kernels)
     /// stores `seq` into slot `me` of every rank's flag array; `launch_wait` (queued before the unpack

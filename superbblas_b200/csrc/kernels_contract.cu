@@ -852,7 +852,8 @@ namespace sbb {
         if (want_dot && (force || p.K.vol >= 1024) && dotk::eligible(desc)) {
             dotk::DotParams dp;
             dotk::build(desc, dp, (long long)sm_count(device) * 2048);
-            if (dotk::threads_of(dp) <= (1ll << 22)) {
+            // (bounds the workspace: 2 bytes per thread with the CTA tree, 256 without)
+            if (dotk::threads_of(dp) <= (dotk::cta_tree(dp) ? (1ll << 26) : (1ll << 20))) {
                 if (describe) {
                     std::stringstream ss;
                     ss << "dot T=" << dp.tvol << " M=" << dp.m << " N=" << dp.n << " K=" << dp.kvol

@@ -43,6 +43,8 @@ namespace sbb {
 
     namespace {
         int g_grid_cap = 0;
+        size_t g_table_bytes = 0; // device memory held by the cached launch tables
+        constexpr size_t kTableBudget = (size_t)1 << 30;
     }
     /// Upper bound on the CTAs of the copy kernels (0 = none).  While an exchange is in flight the
     /// runtime leaves some SMs free so that NCCL's kernels can run beside the pack/unpack kernels.
@@ -268,11 +270,16 @@ namespace sbb {
             permute_kernel(const __grid_constant__ PermParams p, const Tables tab,
                            const typename Op::T *__restrict__ src, typename Op::Q *dst, Op op,
                            const float *__restrict__ ma, const float *__restrict__ mb,
-                           const ExchangeSync xs) {
+                           const bool ma_src, const ExchangeSync xs) {
             using T = typename Op::T;
             using Q = typename Op::Q;
             extern __shared__ __align__(16) unsigned char smem_raw[];
             T *smem = reinterpret_cast<T *>(smem_raw);
+            // ma_src: `ma` is the SOURCE's mask (laid out like the source): it is read with the source
+            // elements and, in the transposing variant, travels to the store slot as one byte per
+            // element through shared memory (after the element tile) -- a masked local copy in one
+            // pass, without first carrying the mask to the destination layout
+            unsigned char *flg = smem_raw + (size_t)p.smem_elems * sizeof(T);
 
             const unsigned tid = threadIdx.x;
             if (blockIdx.x >= p.ntiles) return; // (never taken: the grid is at most ntiles)
@@ -352,11 +359,17 @@ namespace sbb {
                 }
                 return t;
             };
+            float fsrc[(MASK && SMEM) ? EPT : 1]; // source mask words, paired with the elements in r
             auto load = [&](const Tile &t, T(&r)[EPT]) {
                 const T *s = src + t.sbase;
 #pragma unroll
                 for (int k = 0; k < EPT; ++k)
                     if (t.mask_l >> k & 1) r[k] = ld_elem<true>(s, so[k]);
+                if (MASK && SMEM && ma_src) {
+#pragma unroll
+                    for (int k = 0; k < ((MASK && SMEM) ? EPT : 1); ++k)
+                        if (t.mask_l >> k & 1) fsrc[k] = ld_elem<true>(ma + t.sbase, so[k]);
+                }
             };
 
             const unsigned G = gridDim.x;
@@ -373,7 +386,8 @@ namespace sbb {
                 for (int k = 0; k < (MASK ? EPT : 1); ++k) {
                     fa[k] = fb[k] = 1.0f;
                     if (t.mask_s >> k & 1) {
-                        if (ma) fa[k] = ld_elem<true>(ma + t.dbase, dof[k]);
+                        if (ma && !ma_src) fa[k] = ld_elem<true>(ma + t.dbase, dof[k]);
+                        if (ma && ma_src && !SMEM) fa[k] = ld_elem<true>(ma + t.sbase, so[k]); // same slot on both sides
                         if (mb) fb[k] = ld_elem<true>(mb + t.dbase, dof[k]);
                     }
                 }
@@ -397,7 +411,17 @@ namespace sbb {
 #pragma unroll
                     for (int k = 0; k < EPT; ++k)
                         if (cur.mask_l >> k & 1) smem[sp[k] >> 16] = r[k];
+                    if (MASK && ma_src) {
+#pragma unroll
+                        for (int k = 0; k < ((MASK && SMEM) ? EPT : 1); ++k)
+                            if (cur.mask_l >> k & 1) flg[sp[k] >> 16] = fsrc[k] != 0.0f;
+                    }
                     __syncthreads();
+                    if (MASK && ma_src) {
+#pragma unroll
+                        for (int k = 0; k < EPT; ++k)
+                            if ((cur.mask_s >> k & 1) && !flg[sp[k] & 0xffffu]) cur.mask_s &= ~(1u << k);
+                    }
                     if (has_next) load(nxt, r), load_masks(nxt); // in flight during the store phase
                     if (op.add()) {
                         Q o[EPT];
@@ -705,12 +729,17 @@ namespace sbb {
             const size_t slot_bytes = (ne * sizeof(unsigned) + 255) / 256 * 256;
             const size_t total = 3 * slot_bytes + tiles.size() * sizeof(long long);
             char *mem = nullptr;
+            if (g_table_bytes + total > kTableBudget) permute_cache_clear(); // bounded: the cache is a convenience
             cuda_check(cudaMalloc((void **)&mem, total), "cudaMalloc (copy tables)");
+            g_table_bytes += total;
             cuda_check(cudaMemcpyAsync(mem, so.data(), ne * sizeof(unsigned), cudaMemcpyHostToDevice, stream), "table upload");
             cuda_check(cudaMemcpyAsync(mem + slot_bytes, dof.data(), ne * sizeof(unsigned), cudaMemcpyHostToDevice, stream), "table upload");
             cuda_check(cudaMemcpyAsync(mem + 2 * slot_bytes, sp.data(), ne * sizeof(unsigned), cudaMemcpyHostToDevice, stream), "table upload");
             cuda_check(cudaMemcpyAsync(mem + 3 * slot_bytes, tiles.data(), tiles.size() * sizeof(long long), cudaMemcpyHostToDevice, stream), "table upload");
-            // pageable sources are staged before cudaMemcpyAsync returns, so the vectors may go away
+            // The cached launch may later run on other streams (auxiliary stream, another call's
+            // stream, a caller's stream through sbk_permute_copy): the tables must be complete in
+            // device memory before anybody can see them.  Once per distinct geometry.
+            cuda_check(cudaStreamSynchronize(stream), "table upload");
             lp.tab.so = (const unsigned *)mem;
             lp.tab.dof = (const unsigned *)(mem + slot_bytes);
             lp.tab.sp = (const unsigned *)(mem + 2 * slot_bytes);
@@ -866,10 +895,12 @@ namespace sbb {
 
         template <class Op, bool MASK = false, int EPT_ = EPT>
         void launch_perm(LaunchPlan &lp, const void *src, void *dst, Op op, int device,
-                         cudaStream_t stream, const float *ma = nullptr, const float *mb = nullptr) {
+                         cudaStream_t stream, const float *ma = nullptr, const float *mb = nullptr,
+                         bool ma_src = false) {
             using T = typename Op::T;
             using Q = typename Op::Q;
-            const size_t smem_bytes = (size_t)lp.p.smem_elems * sizeof(T);
+            // (masked, transposing: one flag byte per tile element behind the element tile)
+            const size_t smem_bytes = (size_t)lp.p.smem_elems * sizeof(T) + (MASK ? (size_t)lp.p.smem_elems : 0);
             auto go = [&](auto kernel) {
                 // resident CTAs per SM for this kernel, cached by dynamic shared-memory size
                 static std::map<size_t, int> ctas;
@@ -883,7 +914,7 @@ namespace sbb {
                 {
                     KernelTimer timer("permute", stream);
                     kernel<<<grid, NT, smem_bytes, stream>>>(lp.p, lp.tab, (const T *)src, (Q *)dst, op,
-                                                             ma, mb, xs);
+                                                             ma, mb, ma_src, xs);
                 }
                 count_launch();
                 cuda_check(cudaGetLastError(), "permute_kernel launch");
@@ -969,10 +1000,10 @@ namespace sbb {
         template <typename T, typename Q>
         void launch_typed(LaunchPlan &lp, const void *src, void *dst, const double *alpha,
                           bool scale, bool add, int device, cudaStream_t stream, const float *ma,
-                          const float *mb) {
+                          const float *mb, bool ma_src) {
             if (ma || mb)
                 launch_perm<ElemOp<T, Q>, true>(lp, src, dst, {make_elem<T>(alpha), scale, add},
-                                                device, stream, ma, mb);
+                                                device, stream, ma, mb, ma_src);
             else
                 launch_perm<ElemOp<T, Q>>(lp, src, dst, {make_elem<T>(alpha), scale, add}, device,
                                           stream);
@@ -1014,7 +1045,7 @@ namespace sbb {
         /// Run one box of at most KD (canonical) dims
         void run_box(const Canon &c0, const void *src, int dt0, void *dst, int dt1,
                      const double *alpha, bool add, int device, cudaStream_t stream,
-                     std::string *describe, const float *ma, const float *mb) {
+                     std::string *describe, const float *ma, const float *mb, bool ma_src) {
             const bool masked = ma || mb; // masks are per element: no widening, typed kernel
             const bool is_zero = alpha[0] == 0 && (alpha[1] == 0 || dt0 == SBB_F32 ||
                                                    dt0 == SBB_F64 || dt0 == SBB_I32);
@@ -1039,8 +1070,11 @@ namespace sbb {
                 put(c0.ss.data(), c0.ss.size() * sizeof(int64_t));
                 put(c0.ds.data(), c0.ds.size() * sizeof(int64_t));
                 put(&c0.rot, sizeof c0.rot);
-                put(&c0.soff, sizeof c0.soff);
-                put(&c0.doff, sizeof c0.doff);
+                // the offsets only matter through what the widening of the element may assume about
+                // them (promote): their residues, not their values -- a sweep of sub-boxes over a big
+                // tensor shares one entry (and one device table) instead of creating one per offset
+                const int res[2] = {(int)(c0.soff & 15), (int)(c0.doff & 15)};
+                put(res, sizeof res);
             }
             auto hit = describe ? cache.end() : cache.find(key);
             auto remember = [&](const Canon &cc, const LaunchPlan &lp, int es) {
@@ -1052,6 +1086,7 @@ namespace sbb {
                 LaunchPlan lp;
                 if (hit != cache.end()) {
                     c = hit->second.c, lp = hit->second.lp, es = hit->second.es;
+                    c.doff = c0.doff / (es / dtype_size(dt1)); // (cached for another offset with the same residue)
                 } else {
                     es = masked ? dtype_size(dt1) : promote(c, dtype_size(dt1), nullptr, dst, false);
                     lp = plan_launch(c, es, NT * EPT, false);
@@ -1063,7 +1098,8 @@ namespace sbb {
                     return;
                 }
                 char *d = (char *)dst + c.doff * es;
-                const float *xa = ma ? ma + c.doff : nullptr, *xb = mb ? mb + c.doff : nullptr;
+                // (no source here: a source-layout mask does not apply to a zero fill)
+                const float *xa = ma && !ma_src ? ma + c.doff : nullptr, *xb = mb ? mb + c.doff : nullptr;
                 if (es == 16) launch_zero<uint4>(lp, d, device, stream, xa, xb);
                 else if (es == 8) launch_zero<uint2>(lp, d, device, stream, xa, xb);
                 else launch_zero<unsigned>(lp, d, device, stream, xa, xb);
@@ -1074,6 +1110,8 @@ namespace sbb {
                 LaunchPlan lp;
                 if (hit != cache.end()) {
                     c = hit->second.c, lp = hit->second.lp, es = hit->second.es;
+                    const int f = es / dtype_size(dt0);
+                    c.soff = c0.soff / f, c.doff = c0.doff / f;
                 } else {
                     es = promote(c, dtype_size(dt0), src, dst, true);
                     lp = plan_launch(c, es, max_tile_for(es), true);
@@ -1126,7 +1164,8 @@ namespace sbb {
 #define SBB_TYPED(DT0, DT1, T, Q)                                                                  \
     if (dt0 == DT0 && dt1 == DT1) {                                                                \
         launch_typed<T, Q>(lp, s, d, alpha, scale, add, device, stream,                            \
-                           ma ? ma + c.doff : nullptr, mb ? mb + c.doff : nullptr);                \
+                           ma ? ma + (ma_src ? c.soff : c.doff) : nullptr, mb ? mb + c.doff : nullptr,    \
+                           ma_src);                                                                \
         return;                                                                                    \
     }
             SBB_TYPED(SBB_F32, SBB_F32, float, float)
@@ -1211,12 +1250,18 @@ namespace sbb {
             }
         }
         prepared_cache().clear();
+        g_table_bytes = 0;
     }
 
     void permute_copy(const sbk_box_desc &box, const void *src, int dt0, void *dst, int dt1,
                       const double *alpha, bool add, int device, cudaStream_t stream,
-                      std::string *describe, const float *ma, const float *mb) {
+                      std::string *describe, const float *ma, const float *mb, const float *mask_src) {
         if (box.nd < 0 || box.nd > SBK_MAX_DIMS) throw std::runtime_error("permute copy: bad nd");
+        const bool ma_src = mask_src != nullptr;
+        if (ma_src) {
+            if (ma) throw std::runtime_error("permute copy: the source mask is given twice");
+            ma = mask_src;
+        }
         if (!convertible(dt0, dt1))
             throw std::runtime_error("permute copy: unsupported type combination");
         const bool is_zero = alpha[0] == 0 && (alpha[1] == 0 || dt0 == SBB_F32 || dt0 == SBB_F64 ||
@@ -1227,7 +1272,7 @@ namespace sbb {
             return;
         }
         if (c.nd <= KD) {
-            run_box(c, src, dt0, dst, dt1, alpha, add, device, stream, describe, ma, mb);
+            run_box(c, src, dt0, dst, dt1, alpha, add, device, stream, describe, ma, mb, ma_src);
             return;
         }
         // More than KD irreducible dims: iterate over the slowest ones on the host
@@ -1245,7 +1290,7 @@ namespace sbb {
                 sub.soff += idx[k] * c.ss[KD + k];
                 sub.doff += idx[k] * c.ds[KD + k];
             }
-            run_box(sub, src, dt0, dst, dt1, alpha, add, device, stream, describe, ma, mb);
+            run_box(sub, src, dt0, dst, dt1, alpha, add, device, stream, describe, ma, mb, ma_src);
             if (describe) return;
             int k = 0;
             for (; k < outer; ++k) {

@@ -97,6 +97,10 @@ namespace sbb {
         int device = 0;
     };
 
+    /// Masks: `mask_b` is the destination's mask; the source's mask comes either as `mask_a`, already
+    /// carried to the destination layout (one per destination component: copies with remote parts),
+    /// or as `mask_src`, one per SOURCE component in the source's own layout (purely local copies:
+    /// applied in the same pass).
     /// A copy in two steps (the reference's Request, dist.h:54-61): begin() queues everything that
     /// does not depend on other ranks -- staging of host components, the pack kernels with their
     /// signal, the local part -- and finish() the rest: waiting for the other ranks' data, the
@@ -105,7 +109,8 @@ namespace sbb {
     public:
         CopyExec(std::shared_ptr<const CopyPlan> plan, const CopyArgs &args, int dtype0, int dtype1,
                  const double *alpha, std::vector<Buffer> v0, std::vector<Buffer> v1, Comm *comm,
-                 const std::vector<Buffer> *mask_a = nullptr, const std::vector<Buffer> *mask_b = nullptr);
+                 const std::vector<Buffer> *mask_a = nullptr, const std::vector<Buffer> *mask_b = nullptr,
+                 const std::vector<Buffer> *mask_src = nullptr);
         ~CopyExec();
         CopyExec(const CopyExec &) = delete;
         CopyExec &operator=(const CopyExec &) = delete;

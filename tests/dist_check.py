@@ -45,10 +45,59 @@ def gloo_exchange(wire, rank, Wt):
     return exchange
 
 
+def stress(n, rank, world, comm, gpu):
+    """Back-to-back exchanges without any host synchronisation in between: a handful of prepared
+    copies of very different sizes (so that consecutive exchanges use different round counts and
+    arena layouts), chosen at random with the same sequence on every rank, with random host delays
+    that differ between ranks (so that ranks run ahead of one another by several exchanges).  The
+    results are compared on the device after every exchange."""
+    import time
+    rng = np.random.default_rng(777)       # shared: which case comes next
+    mine = np.random.default_rng(1000 + rank)  # private: my delays
+    prepared = []
+    sizes = [(4, 4, 4, 8, 2), (8, 8, 8, 16, 12), (16, 16, 16, 32, 12), (6, 10, 4, 8, 3)]
+    pz = 2 if world % 2 == 0 else 1
+    pt = world // pz
+    for si, (lx, ly, lz, lt, inner) in enumerate(sizes):
+        dim = [lx, ly, lz * pz, lt * pt, inner]
+        pa = sb.basic_partitioning("xyztn", dim, [1, 1, 1, world, 1], "t", world, 1)
+        pb = sb.basic_partitioning("xyztn", dim, [1, 1, pz, pt, 1], "zt", world, 1)
+        for (p0, p1, from1, add) in [(pa, pb, [0] * 5, 0), (pb, pb, [0, 0, 1, 1, 0], 0), (pb, pa, [1, 0, 0, 0, 0], 1)]:
+            case = dict(alpha=1, p0=p0, o0="xyztn", from0=[0] * 5, size0=dim, dim0=dim, p1=p1, o1="xyztn",
+                        from1=from1, dim1=dim, co=1, copyadd=add, T=np.dtype(np.complex64),
+                        Q=np.dtype(np.complex64))
+            v0, v1 = C.make_copy_data(case, 40 + si)
+            want = C.oracle_copy(case, v0, v1)
+            prepared.append(dict(case=case, src=torch.from_numpy(v0[rank].copy()).cuda(),
+                                 init=torch.from_numpy(v1[rank].copy()).cuda(),
+                                 want=torch.from_numpy(want[rank].copy()).cuda()))
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    stream = torch.cuda.ExternalStream(sb.get_stream(torch.cuda.current_device()))
+    with torch.cuda.stream(stream):
+        for it in range(n):
+            pcase = prepared[int(rng.integers(len(prepared)))]
+            case = pcase["case"]
+            dst = pcase["init"].clone()
+            if mine.random() < 0.3:
+                time.sleep(float(mine.random()) * 2e-3)
+            sb.copy(1, case["p0"], 1, case["o0"], case["from0"], case["size0"], case["dim0"], [pcase["src"]],
+                    None, gpu, case["p1"], 1, case["o1"], case["from1"], case["dim1"], [dst], None, gpu,
+                    case["co"], case["copyadd"], comm=comm)
+            bad += (dst.view(torch.int64) != pcase["want"].view(torch.int64)).any().to(torch.int64)
+    sb.sync(gpu)
+    torch.cuda.synchronize()
+    nbad = int(bad.item())
+    print("rank %d: stress %d exchanges, %d wrong" % (rank, n, nbad), flush=True)
+    return nbad
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--backend", default="gloo")
     ap.add_argument("--cases", type=int, default=30)
+    ap.add_argument("--stress", type=int, default=0,
+                    help="nccl only: this many back-to-back exchanges of mixed sizes with random "
+                         "per-rank delays, every result compared bit for bit (flag protocol, arena halves)")
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -117,6 +166,8 @@ def main():
             if not C.bits_equal(g, want[rank * nc1 + j]):
                 bad += 1
                 print("rank %d: copy case %d part %d differs" % (rank, it, j), flush=True)
+    if args.backend == "nccl" and args.stress > 0:
+        bad += stress(args.stress, rank, world, comm, gpu)
     if args.backend == "nccl":
         # distributed contractions: partitions over `world` ranks, reduction of partial sums
         for it in range(args.cases):

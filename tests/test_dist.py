@@ -10,10 +10,11 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def launch(n, backend, cases, port, timeout=600):
+def launch(n, backend, cases, port, timeout=600, stress=0):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tests", "dist_check.py"), "--backend", backend, "--cases", str(cases)]
+           os.path.join(ROOT, "tests", "dist_check.py"), "--backend", backend, "--cases", str(cases),
+           "--stress", str(stress)]
     # tiny pipeline pieces so that the cutting of remote boxes is exercised by the small test cases
     env = dict(os.environ, OMP_NUM_THREADS="1", SBB_CHUNK_BYTES="256")
     # own session, so that a hang can be ended together with every worker process (a worker left
@@ -41,4 +42,4 @@ def test_nccl_world():
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
-    launch(min(n, 8), "nccl", 20, 29531, timeout=300)
+    launch(min(n, 8), "nccl", 20, 29531, timeout=300, stress=300)
