@@ -606,6 +606,9 @@ def main():
     if rank == 0:
         summary = {k: {"GB/s_per_gpu": v["GB/s"] / world, "frac_of_hbm": v["per_gpu_frac_of_hbm"]}
                    for k, v in extras.items() if isinstance(v, dict) and "per_gpu_frac_of_hbm" in v}
+        for k, v in (extras.get("config1") or {}).items():
+            checks["config1_" + k] = v["check"]
+        result_check = all(bool(v) for v in checks.values())
         line = {
             "metric": "contraction TFLOP/s (distillation V^H V -> [t,n,m])",
             "value": hd["value"], "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -668,6 +671,45 @@ def index_field(torch, dev, box, dim, shift, cplx_dtype):
     return torch.view_as_complex(out)
 
 
+def config1_block(E):
+    """BASELINE configs[0] (the reference's own CPU-runnable case) on the GPU: the permutation
+    "xyztsc" -> "cstzyx" and the contractions over s,c on an 8^3 x 16 complex-double lattice
+    (1.5 MB tensors: launch-latency bound; microseconds per call, device time between events)."""
+    sb, torch, dev, gpu, timed = E.sb, E.torch, E.dev, E.gpu, E.timed
+    dim = [8, 8, 8, 16, 4, 3]
+    one = lambda d: np.array([[[0] * len(d), list(d)]], dtype=np.int32)  # noqa: E731
+    rnd = lambda n: torch.view_as_complex(torch.rand(n, 2, device=dev, dtype=torch.float64) * 2 - 1)  # noqa: E731
+    out = {}
+    n = int(np.prod(dim))
+    x, y = rnd(n), torch.zeros(n, device=dev, dtype=torch.complex128)
+    dim1 = dim[::-1]
+    ms = timed(lambda: sb.copy(1, one(dim), 1, "xyztsc", [0] * 6, dim, dim, [x], None, gpu, one(dim1), 1,
+                               "cstzyx", [0] * 6, dim1, [y], None, gpu, sb.FastToSlow, sb.Copy), 100, 10)
+    ok = torch.equal(y.view(8, 8, 8, 16, 4, 3), x.view(3, 4, 16, 8, 8, 8).permute(5, 4, 3, 2, 1, 0))
+    out["permute_xyztsc_cstzyx_c128"] = {"us_per_call": ms * 10, "GB/s": 2 * n * 16 / (ms / 100) / 1e6,
+                                         "check": bool(ok)}
+    for name, o0, d0, o1, d1, o_r, dr in (
+            ("site_contraction_sc", "xyztsc", dim, "xyztsc", dim, "xyzt", dim[:4]),
+            ("contract_cpp_style_n4", "xyztscN", dim + [4], "xyztscn", dim + [4], "xyztNn", dim[:4] + [4, 4])):
+        a, b = rnd(int(np.prod(d0))), rnd(int(np.prod(d1)))
+        r = torch.zeros(int(np.prod(dr)), device=dev, dtype=torch.complex128)
+        ms = timed(lambda: sb.contraction(1, one(d0), [0] * len(d0), d0, d0, 1, o0, True, [a], gpu, one(d1),
+                                          [0] * len(d1), d1, d1, 1, o1, False, [b], gpu, 0, one(dr),
+                                          [0] * len(dr), dr, dr, 1, o_r, [r], gpu, sb.FastToSlow), 100, 10)
+        # FastToSlow: x fastest; the contracted (s,c) are the slowest labels of the operands
+        A = a.view(*(d0[::-1]))
+        B = b.view(*(d1[::-1]))
+        if len(d0) == 6:
+            ref = torch.einsum("cstzyx,cstzyx->tzyx", A.conj(), B)
+        else:
+            ref = torch.einsum("Ncstzyx,ncstzyx->nNtzyx", A.conj(), B)
+        err = float((torch.linalg.norm(r - ref.reshape(-1)) / torch.linalg.norm(ref)).item())
+        flop = 8.0 * np.prod(dr) * 12
+        out[name] = {"us_per_call": ms * 10, "GFLOP/s": flop / (ms / 100) / 1e6, "rel_err": err,
+                     "check": bool(err < 1e-12)}
+    return out
+
+
 def reshuffle_extras(E, hbm_peak, checks):
     """Reshuffle GB/s = moved elements x (sizeof T + sizeof Q) / time (the reference's `memops`,
     tensor.h:1087): label permutation, periodic shift, and (N > 1) redistribution t -> (z,t).
@@ -726,6 +768,8 @@ def reshuffle_extras(E, hbm_peak, checks):
         checks["masked_permute"] = bool(torch.equal(y.view(32, 32, 32, 64, 4, 3), want))
         del m0, m1, want
     del x, y
+    if world == 1:
+        out["config1"] = config1_block(E)
     # (b) periodic +1 shifts of a 64^3 x 128 x 4 x 3 field distributed on z,t (config 5): per GPU block
     pz, pt = grid_for(world)
     for es, tag in ((8, "c64"), (16, "c128")):

@@ -488,6 +488,109 @@ namespace superbblas {
     }
 #endif
 
+    // ---- SB_DEBUG >= 2: every copy first verifies itself on mock tensors (reference: ns_copy_test,
+    //      dist.h:1919-2116, called from copy_request at dist.h:2282-2285) ------------------------------
+    template <std::size_t Nd0, std::size_t Nd1, typename T, typename Q>
+    void copy(typename detail::elem<T>::type alpha, const PartitionItem<Nd0> *p0, int ncomponents0,
+              const char *o0, const Coor<Nd0> &from0, const Coor<Nd0> &size0, const Coor<Nd0> &dim0,
+              const T **v0, const MaskType **mask0, const Context *ctx0,
+              const PartitionItem<Nd1> *p1, int ncomponents1, const char *o1,
+              const Coor<Nd1> &from1, const Coor<Nd1> &dim1, Q **v1, const MaskType **mask1,
+              const Context *ctx1, sbb_comm_t comm, CoorOrder co, CopyAdd copyadd,
+              Request *request = nullptr, Session session = 0);
+
+    namespace detail {
+        inline bool &inside_self_check() {
+            static bool v = false;
+            return v;
+        }
+
+        /// The same copy on host tensors of doubles whose elements hold the global linear index of
+        /// their own coordinate; afterwards every local destination element must hold the index of
+        /// the source coordinate it comes from (times the number of holders for Add; 0 where a Copy
+        /// has no holder; the sentinel outside the range).  The mock tensors go through the whole
+        /// path (staging, kernels, exchange between ranks).  Collective like the copy itself.
+        template <std::size_t Nd0, std::size_t Nd1>
+        void self_check_copy(const PartitionItem<Nd0> *p0, int nc0, const char *o0, const Coor<Nd0> &from0,
+                             const Coor<Nd0> &size0, const Coor<Nd0> &dim0, const PartitionItem<Nd1> *p1,
+                             int nc1, const char *o1, const Coor<Nd1> &from1, const Coor<Nd1> &dim1,
+                             sbb_comm_t comm, CoorOrder co, CopyAdd copyadd) {
+            if (inside_self_check()) return;
+            struct Guard {
+                Guard() { inside_self_check() = true; }
+                ~Guard() { inside_self_check() = false; }
+            } guard;
+            int rank = 0, nranks = 1;
+            if (comm) check(sbb_comm_rank(comm, &rank, &nranks));
+            const double sentinel = -1.0;
+            const Coor<Nd0, long long> g0 = get_strides<long long>(dim0, co);
+            std::vector<std::vector<double>> m0(nc0), m1(nc1);
+            for (int c = 0; c < nc0; ++c) {
+                const PartitionItem<Nd0> &b = p0[(std::size_t)rank * nc0 + c];
+                const std::size_t vol = volume<Nd0>(b[1]);
+                const Coor<Nd0, long long> ls = get_strides<long long>(b[1], co);
+                m0[c].resize(vol);
+                for (std::size_t i = 0; i < vol; ++i) {
+                    Coor<Nd0> x = index2coor<Nd0, int, long long>((long long)i, b[1], ls);
+                    for (std::size_t k = 0; k < Nd0; ++k) x[k] = (x[k] + b[0][k]) % dim0[k];
+                    m0[c][i] = (double)coor2index<Nd0, int, long long>(x, dim0, g0);
+                }
+            }
+            for (int c = 0; c < nc1; ++c)
+                m1[c].assign(volume<Nd1>(p1[(std::size_t)rank * nc1 + c][1]), sentinel);
+            std::vector<const double *> s(nc0);
+            std::vector<double *> d(nc1);
+            for (int c = 0; c < nc0; ++c) s[c] = m0[c].data();
+            for (int c = 0; c < nc1; ++c) d[c] = m1[c].data();
+            std::vector<Context> c0(nc0, Context{CPU, CPU_DEVICE_ID}), c1(nc1, Context{CPU, CPU_DEVICE_ID});
+            superbblas::copy<Nd0, Nd1, double, double>(1.0, p0, nc0, o0, from0, size0, dim0, s.data(), nullptr,
+                                                       c0.data(), p1, nc1, o1, from1, dim1, d.data(), nullptr,
+                                                       c1.data(), comm, co, copyadd, nullptr, 0);
+            // position of every destination label in the source order (-1: absent, extent 1)
+            int pos0[Nd1 ? Nd1 : 1];
+            for (std::size_t k1 = 0; k1 < Nd1; ++k1) {
+                pos0[k1] = -1;
+                for (std::size_t k0 = 0; k0 < Nd0; ++k0)
+                    if (o0[k0] == o1[k1]) pos0[k1] = (int)k0;
+            }
+            for (int c = 0; c < nc1; ++c) {
+                const PartitionItem<Nd1> &b = p1[(std::size_t)rank * nc1 + c];
+                const Coor<Nd1, long long> ls = get_strides<long long>(b[1], co);
+                for (std::size_t i = 0; i < m1[c].size(); ++i) {
+                    Coor<Nd1> y = index2coor<Nd1, int, long long>((long long)i, b[1], ls);
+                    Coor<Nd0> x = from0;
+                    bool in_range = true;
+                    for (std::size_t k1 = 0; k1 < Nd1 && in_range; ++k1) {
+                        const int g = (y[k1] + b[0][k1]) % dim1[k1];
+                        const int rel = ((g - from1[k1]) % dim1[k1] + dim1[k1]) % dim1[k1];
+                        const int extent = pos0[k1] >= 0 ? size0[pos0[k1]] : 1;
+                        if (rel >= extent) in_range = false;
+                        else if (pos0[k1] >= 0) x[pos0[k1]] = (from0[pos0[k1]] + rel) % dim0[pos0[k1]];
+                    }
+                    double want = sentinel;
+                    if (in_range) {
+                        int rep = 0;
+                        for (std::size_t q = 0; q < (std::size_t)nranks * nc0; ++q) {
+                            bool holds = true;
+                            for (std::size_t k = 0; k < Nd0 && holds; ++k) {
+                                const int sz = p0[q][1][k];
+                                const int rel = ((x[k] - p0[q][0][k]) % dim0[k] + dim0[k]) % dim0[k];
+                                holds = sz > 0 && (sz >= dim0[k] || rel < sz);
+                            }
+                            rep += holds;
+                        }
+                        const double idx = (double)coor2index<Nd0, int, long long>(x, dim0, g0);
+                        want = copyadd == Copy ? (rep ? idx : 0.0) : sentinel + rep * idx;
+                    }
+                    if (m1[c][i] != want)
+                        throw std::runtime_error("SB_DEBUG self-check of copy failed: component " +
+                                                 std::to_string(c) + " element " + std::to_string(i) + " holds " +
+                                                 std::to_string(m1[c][i]) + ", expected " + std::to_string(want));
+                }
+            }
+        }
+    }
+
     // ---- copy ------------------------------------------------------------------------------------------
 
     /// Copy the content of plural tensor v0 into v1 (reference: dist.h:3534 with the communicator
@@ -499,10 +602,13 @@ namespace superbblas {
               const PartitionItem<Nd1> *p1, int ncomponents1, const char *o1,
               const Coor<Nd1> &from1, const Coor<Nd1> &dim1, Q **v1, const MaskType **mask1,
               const Context *ctx1, sbb_comm_t comm, CoorOrder co, CopyAdd copyadd,
-              Request *request = nullptr, Session session = 0) {
+              Request *request, Session session) {
         if (session != 0) throw std::runtime_error("unsupported session");
         detail::check_order<Nd0>(o0, "o0");
         detail::check_order<Nd1>(o1, "o1");
+        if (getDebugLevel() >= 2 && !mask0 && !mask1)
+            detail::self_check_copy<Nd0, Nd1>(p0, ncomponents0, o0, from0, size0, dim0, p1, ncomponents1, o1,
+                                              from1, dim1, comm, co, copyadd);
         const auto a = detail::scalar(alpha);
         if (request) {
             // deferred completion (dist.h:3554-3557): the packs, their signal and the local part are

@@ -52,6 +52,23 @@ def test_reference_own_dist_program():
     assert ">>> GPU tests:" in r.stdout and "Time in copying halos out" in r.stdout
 
 
+def test_sb_debug_2_self_check_of_every_copy():
+    """SB_DEBUG=2 (reference: tests/Makefile:78-79 runs its dist test that way; dist.h:2282-2285):
+    every copy of the reference's tests/dist.cpp and of the drop-in program first verifies itself on
+    index-valued mock tensors through the whole path; a wrong element throws."""
+    env = dict(os.environ, SB_DEBUG="2")
+    exe = os.path.join(HERE, "cxx", "dropin_test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and "Everything went ok!" in r.stdout, (r.stdout + r.stderr)[-2000:]
+    exe = os.path.join(HERE, "cxx", "ref_dist_wrapper")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cxx/ref_dist_wrapper not built (needs /root/reference at build time)")
+    r = subprocess.run([exe, "--dim=4 4 4 8 4", "--reps=1"], capture_output=True, text=True, timeout=600,
+                       env=env)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    assert "Time in copying halos out" in r.stdout
+
+
 # The wrapper also accepts --components=N (several components per process) and --cpu (host contexts,
 # staged through the GPU); they run the same enumeration but take much longer, so they are not part of
 # the default GPU test run.
