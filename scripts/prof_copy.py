@@ -37,4 +37,21 @@ if which in ("all", "shiftx"):
     case("xyztsc", [64, 64, 32, 32, 4, 3], "xyztsc", torch.complex64, [1, 0, 0, 0, 0, 0])
 if which in ("all", "shiftt"):
     case("xyztsc", [64, 64, 32, 32, 4, 3], "xyztsc", torch.complex64, [0, 0, 0, 1, 0, 0])
+if which in ("masked",):
+    # even-site masks on both sides of the xyztsc -> cstzyx permutation (one pass: source mask read with the data)
+    dim0 = [32, 32, 32, 64, 4, 3]
+    dim1 = dim0[::-1]
+    vol = int(np.prod(dim0))
+    x = torch.view_as_complex(torch.rand(vol, 2, device="cuda", dtype=torch.float64))
+    y = torch.zeros_like(x)
+    idx = torch.arange(vol, device="cuda")
+    par = (idx % 32 + (idx // 32) % 32 + (idx // 1024) % 32 + (idx // 32768) % 64) % 2
+    m0 = (par == 0).to(torch.float32)
+    m1 = m0.view(3, 4, 64, 32, 32, 32).permute(5, 4, 3, 2, 1, 0).contiguous().view(-1)
+    p0 = np.array([[[0] * 6, dim0]], dtype=np.int32)
+    p1 = np.array([[[0] * 6, dim1]], dtype=np.int32)
+    for _ in range(2):
+        sb.copy(1, p0, 1, "xyztsc", [0] * 6, dim0, dim0, [x], [m0], gpu, p1, 1, "cstzyx", [0] * 6, dim1, [y],
+                [m1], gpu, sb.FastToSlow, sb.Copy)
+    sb.sync(gpu)
 print("done")

@@ -68,6 +68,10 @@ namespace sbb {
         constexpr int MAXT = 6; // tiled dims
         constexpr int NT = 256; // threads per CTA
         constexpr int EPT = 8;  // slots (elements of a tile) per thread; 16 was measured slower for transposing tiles
+        // Masked copies carry up to three mask words per slot besides the element and the slot maps:
+        // with 8 slots the 16-byte variant needs > 128 registers (measured: spills, 2 CTAs per SM,
+        // 25 % occupancy, 0.43 ms for the even-site permutation).  4 slots: 3 CTAs per SM.
+        constexpr int MASK_EPT = 4;
 
         struct PermParams {
             int nd, nt, tile_elems, smem_elems;
@@ -359,16 +363,17 @@ namespace sbb {
                 }
                 return t;
             };
-            float fsrc[(MASK && SMEM) ? EPT : 1]; // source mask words, paired with the elements in r
-            auto load = [&](const Tile &t, T(&r)[EPT]) {
+            constexpr int NFS = (MASK && SMEM) ? EPT : 1;
+            float fsrc[NFS]; // source mask words, paired with the elements in r
+            auto load = [&](const Tile &t, T(&r)[EPT], float(&fs)[NFS]) {
                 const T *s = src + t.sbase;
 #pragma unroll
                 for (int k = 0; k < EPT; ++k)
                     if (t.mask_l >> k & 1) r[k] = ld_elem<true>(s, so[k]);
                 if (MASK && SMEM && ma_src) {
 #pragma unroll
-                    for (int k = 0; k < ((MASK && SMEM) ? EPT : 1); ++k)
-                        if (t.mask_l >> k & 1) fsrc[k] = ld_elem<true>(ma + t.sbase, so[k]);
+                    for (int k = 0; k < NFS; ++k)
+                        if (t.mask_l >> k & 1) fs[k] = ld_elem<true>(ma + t.sbase, so[k]);
                 }
             };
 
@@ -393,7 +398,7 @@ namespace sbb {
                 }
             };
             T r[EPT];
-            load(cur, r);
+            load(cur, r, fsrc);
             load_masks(cur);
             for (unsigned i = 0; i < my_tiles; ++i, tile += G) {
                 const bool has_next = i + 1 < my_tiles;
@@ -413,7 +418,7 @@ namespace sbb {
                         if (cur.mask_l >> k & 1) smem[sp[k] >> 16] = r[k];
                     if (MASK && ma_src) {
 #pragma unroll
-                        for (int k = 0; k < ((MASK && SMEM) ? EPT : 1); ++k)
+                        for (int k = 0; k < NFS; ++k)
                             if (cur.mask_l >> k & 1) flg[sp[k] >> 16] = fsrc[k] != 0.0f;
                     }
                     __syncthreads();
@@ -422,7 +427,7 @@ namespace sbb {
                         for (int k = 0; k < EPT; ++k)
                             if ((cur.mask_s >> k & 1) && !flg[sp[k] & 0xffffu]) cur.mask_s &= ~(1u << k);
                     }
-                    if (has_next) load(nxt, r), load_masks(nxt); // in flight during the store phase
+                    if (has_next) load(nxt, r, fsrc), load_masks(nxt); // in flight during the store phase
                     if (op.add()) {
                         Q o[EPT];
 #pragma unroll
@@ -440,7 +445,7 @@ namespace sbb {
                     __syncthreads();
                 } else {
                     T r2[EPT];
-                    if (has_next) load(nxt, r2), load_masks(nxt);
+                    if (has_next) load(nxt, r2, fsrc), load_masks(nxt);
                     if (op.add()) {
                         Q o[EPT];
 #pragma unroll
@@ -920,7 +925,7 @@ namespace sbb {
                 cuda_check(cudaGetLastError(), "permute_kernel launch");
             };
             // small elements: three resident CTAs per SM (more loads in flight per SM for the same bytes)
-            constexpr int MINB = (sizeof(T) <= 8 && sizeof(Q) <= 8 && EPT_ <= 8 && !MASK) ? 3 : 2;
+            constexpr int MINB = ((sizeof(T) <= 8 && sizeof(Q) <= 8 && EPT_ <= 8 && !MASK) || (MASK && EPT_ <= 4)) ? 3 : 2;
             if (lp.smem)
                 go(permute_kernel<Op, true, EPT_, MINB, MASK>);
             else
@@ -1001,9 +1006,9 @@ namespace sbb {
         void launch_typed(LaunchPlan &lp, const void *src, void *dst, const double *alpha,
                           bool scale, bool add, int device, cudaStream_t stream, const float *ma,
                           const float *mb, bool ma_src) {
-            if (ma || mb)
-                launch_perm<ElemOp<T, Q>, true>(lp, src, dst, {make_elem<T>(alpha), scale, add},
-                                                device, stream, ma, mb, ma_src);
+            if (ma || mb) // (planned with MASK_EPT slots per thread, see run_box)
+                launch_perm<ElemOp<T, Q>, true, MASK_EPT>(lp, src, dst, {make_elem<T>(alpha), scale, add},
+                                                          device, stream, ma, mb, ma_src);
             else
                 launch_perm<ElemOp<T, Q>>(lp, src, dst, {make_elem<T>(alpha), scale, add}, device,
                                           stream);
@@ -1145,7 +1150,7 @@ namespace sbb {
             if (hit != cache.end()) {
                 lp = hit->second.lp;
             } else {
-                lp = plan_launch(c, std::max(es0, es1), NT * EPT, true);
+                lp = plan_launch(c, std::max(es0, es1), NT * (masked ? MASK_EPT : EPT), true);
                 if (!describe) {
                     build_tables(lp, true, device, stream);
                     remember(c, lp, 0);

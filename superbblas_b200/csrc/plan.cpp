@@ -316,6 +316,38 @@ namespace sbb {
             }
             plan->arena_elems = std::max(plan->arena_elems, off);
         }
+        // Phases of the exchange: greedy edge colouring -- every edge (sender -> receiver) takes the
+        // smallest phase not yet used at its sender or at its receiver.  Edges of the senders with the
+        // fewest messages are coloured first: nothing synchronises the phases in time, every sender
+        // simply starts with its phase 0, so a sender with a single message must own phase 0 at its
+        // receiver (a redistribution t-slabs -> (z,t) blocks on 8 ranks: ranks 0 and 7 keep half of
+        // their data and send one message; coloured in rank order rank 7 got phase 1, sent at once
+        // and collided with rank 6 for half of the exchange).
+        plan->send_phase.assign(a.nranks, 0);
+        {
+            std::vector<int> outdeg(a.nranks, 0);
+            std::vector<std::pair<int, int>> edges;
+            for (int r = 0; r < a.nranks; ++r)
+                for (int q = 0; q < a.nranks; ++q)
+                    if (r != q && wire(r, q) > 0) ++outdeg[r], edges.emplace_back(r, q);
+            std::stable_sort(edges.begin(), edges.end(), [&](const std::pair<int, int> &x, const std::pair<int, int> &y) {
+                return outdeg[x.first] < outdeg[y.first];
+            });
+            std::vector<std::vector<char>> used_s(a.nranks), used_r(a.nranks);
+            for (const auto &e : edges) {
+                const int r = e.first, q = e.second;
+                size_t c = 0;
+                for (;; ++c) {
+                    const bool bs = c < used_s[r].size() && used_s[r][c];
+                    const bool br = c < used_r[q].size() && used_r[q][c];
+                    if (!bs && !br) break;
+                }
+                if (used_s[r].size() <= c) used_s[r].resize(c + 1, 0);
+                if (used_r[q].size() <= c) used_r[q].resize(c + 1, 0);
+                used_s[r][c] = used_r[q][c] = 1;
+                if (r == me) plan->send_phase[q] = (int)c;
+            }
+        }
         return plan;
     }
 

@@ -44,6 +44,10 @@ namespace sbb {
         std::vector<int64_t> send_seg_off, recv_seg_off;
         int64_t arena_elems = 0;
         int64_t max_pair_elems = 0; ///< longest message of the whole exchange (all ranks agree)
+        /// Phase of my message to every peer: a proper colouring of the edges of the exchange
+        /// (sender -> receiver pairs), computed identically on every rank, so that senders that
+        /// visit their receivers in phase order do not meet at a receiver (index = peer rank)
+        std::vector<int> send_phase;
         std::string describe() const;
     };
 

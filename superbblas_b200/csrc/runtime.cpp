@@ -950,11 +950,12 @@ namespace sbb {
         local_done = args.add; // additions keep plan order: everything after the last wait
         for (int k = 0; k < nrounds; ++k) {
             set_grid_cap(pack_grid());
-            // Order of the receivers inside a round: ascending, rotated by my rank.  With the same
-            // order on every rank all senders of a redistribution hit the same receivers at the same
-            // time (t-slabs -> (z,t) blocks on 8 GPUs: everybody first sends to the z = 0 ranks, two
-            // senders per receiver at half the link rate each, while the z = 1 ranks idle: measured
-            // 312 GB/s per direction); rotated, the senders of a receiver take turns.
+            // Order of the receivers inside a round: by the phase the planner gave every message (a
+            // proper colouring of the sender -> receiver pairs, identical on all ranks).  With the
+            // same order on every rank all senders of a redistribution hit the same receivers at the
+            // same time (t-slabs -> (z,t) blocks on 8 GPUs: everybody first sends to the z = 0 ranks,
+            // two senders per receiver at half the link rate each, while the z = 1 ranks idle:
+            // 312 GB/s per direction; rotating the order by the rank left two such collisions: 444).
             std::vector<const BoxOp *> packs;
             {
                 std::vector<int> peers;
@@ -962,8 +963,10 @@ namespace sbb {
                     if (op.kind == BoxOp::Pack && round_of(op) == k &&
                         std::find(peers.begin(), peers.end(), op.peer) == peers.end())
                         peers.push_back(op.peer);
-                std::sort(peers.begin(), peers.end());
-                if (!peers.empty()) std::rotate(peers.begin(), peers.begin() + comm->rank % (int)peers.size(), peers.end());
+                std::sort(peers.begin(), peers.end(), [&](int x, int y) {
+                    const int px = pl.send_phase[x], py = pl.send_phase[y];
+                    return px != py ? px < py : x < y;
+                });
                 for (int peer : peers)
                     for (const auto &op : pl.ops)
                         if (op.kind == BoxOp::Pack && round_of(op) == k && op.peer == peer) packs.push_back(&op);
