@@ -504,6 +504,16 @@ def main():
         rf = torch.zeros(nout, device=dev, dtype=torch.complex64)
         stepf = lambda: contraction_step(E, head, pv, pr, af, bf, rf, gpu)  # noqa: E731
         ms_f = timed(stepf, 10, 3)
+        # the SM clock under this kernel (TMA + tensor cores + shared memory + HBM all busy: the 1 kW
+        # power cap shows here first): a 2 s loop with the sampler on
+        csamp = ClockSampler(local)
+        csamp.start()
+        t_end = time.time() + 2.0
+        while time.time() < t_end:
+            for _ in range(50):
+                stepf()
+            sb.sync(gpu)
+        clocks_c64 = csamp.stop()
         sb.profile_enable(True)
         sb.profile_read("contract_tc")
         timed(stepf, 10, 1)
@@ -517,7 +527,7 @@ def main():
         contraction_c64 = {"TFLOP/s": head.flop * 10 / (ms_f * 1e-3) / 1e12, "ms": ms_f / 10,
                            "rel_err_vs_c128": err_f, "min_bytes": min_bytes,
                            "kernel": "contract_tc_kernel (TMA + tcgen05 kind::tf32 x3, TMEM accumulators)",
-                           "kernel_ms": kms_f / max(kn_f, 1),
+                           "kernel_ms": kms_f / max(kn_f, 1), "clocks_under_this_kernel": clocks_c64,
                            "hbm_floor_ms": hbm_floor_ms,
                            "frac_of_hbm_roofline": hbm_floor_ms / (ms_f / 10),
                            "kernel_frac_of_hbm_roofline": hbm_floor_ms / (kms_f / max(kn_f, 1)) if kn_f else None}

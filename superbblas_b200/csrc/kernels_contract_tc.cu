@@ -17,17 +17,17 @@
 //    2^-19 |accumulator| (relative error of a chain of n instructions ~ 1.9e-6 sqrt(n/2); the first
 //    version of this kernel, one chain of 4096 instructions per CTA, was off by 8e-5).  So the
 //    tensor core only sums SHORT chains: the hi*hi products go to an accumulator H that is drained
-//    ("promoted") every `promote` stages by four accumulation warps, which keep the running sums in
+//    ("promoted") every `promote` stages by eight accumulation warps, which keep the running sums in
 //    FP32 registers (IEEE adds on the CUDA cores); H is double buffered in TMEM so that the tensor
 //    core never waits for the drain.  The hi*lo + lo*hi products, 2^-11 smaller, accumulate in a
 //    third TMEM region S for the whole K slice (their accumulation error is 2^-11 smaller too).
 //    K is also split across CTAs and the slices are summed in double by the reduce kernel.
 //  * Data path per CTA (one 64 x 64 complex tile of one batch entry and one K slice; 1 CTA per SM):
 //      TMA (cp.async.bulk.tensor, 64 rows x 32 complex per operand) -> raw ring (3 stages)
-//      -> 4 transform warps (LDS.128 / split / STS.128 into the K-major SWIZZLE_128B layout the
+//      -> 8 transform warps (LDS.128 / split / STS.128 into the K-major SWIZZLE_128B layout the
 //         tensor core reads) -> operand ring (2 stages x {Ahi, Alo, Bhi, Blo})
 //      -> 1 thread issues tcgen05.mma.kind::tf32 (M = N = 128, K = 8 per instruction, 12 per stage)
-//      -> 128 x 128 FP32 accumulators in TMEM (H[2], S) -> tcgen05.ld by 4 accumulation warps
+//      -> 128 x 128 FP32 accumulators in TMEM (H[2], S) -> tcgen05.ld by 8 accumulation warps
 //         -> FP32 running sums in registers -> workspace.
 //    All hand-offs are mbarriers (TMA transaction counts, tcgen05.commit); no __syncthreads in the
 //    main loop.
@@ -58,7 +58,12 @@ namespace sbb {
             constexpr int RAW_STAGE = 2 * RAW_TILE, OP_STAGE = 4 * OP_TILE;
             constexpr int SMEM_DATA = OP_STAGES * OP_STAGE + RAW_STAGES * RAW_STAGE;
             constexpr int SMEM_BYTES = SMEM_DATA + 1024 /* alignment slack */ + 256 /* barriers */;
-            constexpr int THREADS = 320;            // warps 0-3 transform, 4-7 accumulate, 8 TMA, 9 MMA
+            // warps 0-7 transform, 8-15 accumulate (two per TMEM lane quadrant), 16 TMA, 17 MMA.  With four
+            // transform warps (one per scheduler) the split -- ~530 dependent instructions per thread
+            // and stage -- took longer than the 768 cycles of the stage's MMAs and bound the kernel
+            // (ncu: issue slots 44 % busy, tensor pipe 53 %, shared memory 53 %, DRAM 61 %).
+            constexpr int THREADS = 576;
+            constexpr int NTR = 256, NACC = 256;    // transform / accumulation threads
             constexpr int TMEM_COLS = 512;          // H[0] at column 0, H[1] at 128, S at 256
 
             struct Params {
@@ -130,6 +135,16 @@ namespace sbb {
                                "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
                                "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
                                "=r"(r[31])
+                             : "r"(taddr)
+                             : "memory");
+            }
+
+            __device__ __forceinline__ void tmem_ld16(unsigned taddr, unsigned *r) {
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                               "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+                               "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                              : "r"(taddr)
                              : "memory");
             }
@@ -222,19 +237,19 @@ namespace sbb {
 
                 // ---- set-up ------------------------------------------------------------------------
                 if (tid == 0) {
-                    for (int s = 0; s < RAW_STAGES; ++s) mbar_init(raw_full(s), 1), mbar_init(raw_empty(s), 128);
-                    for (int u = 0; u < OP_STAGES; ++u) mbar_init(op_full(u), 128), mbar_init(op_empty(u), 1);
-                    for (int b = 0; b < 2; ++b) mbar_init(acc_full(b), 1), mbar_init(acc_empty(b), 128);
+                    for (int s = 0; s < RAW_STAGES; ++s) mbar_init(raw_full(s), 1), mbar_init(raw_empty(s), NTR);
+                    for (int u = 0; u < OP_STAGES; ++u) mbar_init(op_full(u), NTR), mbar_init(op_empty(u), 1);
+                    for (int b = 0; b < 2; ++b) mbar_init(acc_full(b), 1), mbar_init(acc_empty(b), NACC);
                     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
                 }
-                if (warp == 9) { // the MMA warp owns the tensor memory
+                if (warp == 17) { // the MMA warp owns the tensor memory
                     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                                      smem_u32(tmem_slot)),
                                  "n"(TMEM_COLS)
                                  : "memory");
                     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
                 }
-                if (warp == 8 && lane == 0) {
+                if (warp == 16 && lane == 0) {
                     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
                     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
                 }
@@ -245,7 +260,7 @@ namespace sbb {
                 const int P = p.promote > 0 ? p.promote : nsteps; // stages per chain
                 const int nchunks = (nsteps + P - 1) / P;
 
-                if (warp == 8) {
+                if (warp == 16) {
                     // ===== TMA producer =================================================================
                     if (lane == 0) {
                         for (int it = 0; it < nsteps; ++it) {
@@ -258,7 +273,7 @@ namespace sbb {
                             tma_load_4d(dst + RAW_TILE, &map_b, kc, nt * TN, t0, t1, raw_full(s));
                         }
                     }
-                } else if (warp == 9) {
+                } else if (warp == 17) {
                     // ===== MMA issuer ===================================================================
                     if (lane == 0) {
                         for (int it = 0; it < nsteps; ++it) {
@@ -284,45 +299,47 @@ namespace sbb {
                             if (last) mma_commit(acc_full(b)); // (the last one also covers S)
                         }
                     }
-                } else if (warp >= 4) {
-                    // ===== accumulation warps (4-7): TMEM lanes 32 (warp % 4) .. +31, one row per thread ====
+                } else if (warp >= 8) {
+                    // ===== accumulation warps (8-15): TMEM lanes 32 (warp % 4) .. +31, one row per thread,
+                    //       columns 64 h .. 64 h + 63 of the 128 with h = (warp - 8) / 4 =====================
                     const unsigned lane_base = (unsigned)((warp & 3) * 32) << 16;
-                    float sum[128];
+                    const unsigned col0 = (unsigned)(((warp - 8) >> 2) * 64);
+                    float sum[64];
 #pragma unroll
-                    for (int j = 0; j < 128; ++j) sum[j] = 0.f;
+                    for (int j = 0; j < 64; ++j) sum[j] = 0.f;
                     for (int c = 0; c < nchunks; ++c) {
                         const int b = c & 1;
                         mbar_wait(acc_full(b), (c >> 1) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            unsigned v[32];
-                            tmem_ld32(tmem + lane_base + (unsigned)(b * 128 + q * 32), v);
+                        for (int q = 0; q < 4; ++q) { // (16 columns at a time: 64 sums + 16 values fit the registers)
+                            unsigned v[16];
+                            tmem_ld16(tmem + lane_base + (unsigned)(b * 128) + col0 + (unsigned)(q * 16), v);
                             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) sum[q * 32 + j] += __uint_as_float(v[j]);
+                            for (int j = 0; j < 16; ++j) sum[q * 16 + j] += __uint_as_float(v[j]);
                         }
                         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                         mbar_arrive(acc_empty(b));
                     }
                     // the small terms (complete: the last acc_full covered them), then the partial tile
                     const long long tile_id = ((t * p.mtiles + mt) * p.ntiles + nt) * (long long)p.ksplit + ks;
-                    float *out = ws + tile_id * (128 * 128) + ((warp & 3) * 32 + lane) * 128;
+                    float *out = ws + tile_id * (128 * 128) + ((warp & 3) * 32 + lane) * 128 + col0;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        unsigned v[32];
-                        tmem_ld32(tmem + lane_base + (unsigned)(256 + q * 32), v);
+                        unsigned v[16];
+                        tmem_ld16(tmem + lane_base + 256u + col0 + (unsigned)(q * 16), v);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4 *>(out + q * 32 + j * 4) =
-                                make_float4(sum[q * 32 + 4 * j] + __uint_as_float(v[4 * j]),
-                                            sum[q * 32 + 4 * j + 1] + __uint_as_float(v[4 * j + 1]),
-                                            sum[q * 32 + 4 * j + 2] + __uint_as_float(v[4 * j + 2]),
-                                            sum[q * 32 + 4 * j + 3] + __uint_as_float(v[4 * j + 3]));
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<float4 *>(out + q * 16 + j * 4) =
+                                make_float4(sum[q * 16 + 4 * j] + __uint_as_float(v[4 * j]),
+                                            sum[q * 16 + 4 * j + 1] + __uint_as_float(v[4 * j + 1]),
+                                            sum[q * 16 + 4 * j + 2] + __uint_as_float(v[4 * j + 2]),
+                                            sum[q * 16 + 4 * j + 3] + __uint_as_float(v[4 * j + 3]));
                     }
                 } else {
-                    // ===== transform warps (0-3) ==========================================================
+                    // ===== transform warps (0-7) ==========================================================
                     // item = (row r, group g of 4 complex): lanes of a quarter warp share r and cover
                     // g = 0..7, i.e. one 256-byte raw row and one 128-byte row of each output tile.
                     // The two 16-byte loads of a thread are issued in swapped order by the upper four
@@ -338,17 +355,17 @@ namespace sbb {
                         for (int half = 0; half < 2; ++half) { // A then B
                             const unsigned src = ra + half * RAW_TILE;
                             const unsigned hi = op + (2 * half) * OP_TILE, lo = hi + OP_TILE;
-                            float4 f[4], h[4];
+                            float4 f[2], h[2];
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int r = (tid >> 3) + 16 * i;
+                            for (int i = 0; i < 2; ++i) {
+                                const int r = (tid >> 3) + 32 * i;
                                 const unsigned b = src + r * (BKC * 8) + g * 32;
                                 f[i] = lds128(b + swap * 16);
                                 h[i] = lds128(b + 16 - swap * 16);
                             }
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int r = (tid >> 3) + 16 * i;
+                            for (int i = 0; i < 2; ++i) {
+                                const int r = (tid >> 3) + 32 * i;
                                 const unsigned off = (unsigned)((r >> 3) * 1024 + (r & 7) * 128 + ((g ^ (r & 7)) << 4));
                                 split_store(swap ? h[i] : f[i], swap ? f[i] : h[i], hi, lo, off);
                             }
@@ -363,250 +380,13 @@ namespace sbb {
                 // ---- teardown ----------------------------------------------------------------------------
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
-                if (warp == 9) {
+                if (warp == 17) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS)
                                  : "memory");
                 }
             }
 
-
-            // ---- variant: the A operand goes through tensor memory ---------------------------------------
-            // The kernel above is bound by shared-memory bandwidth (ncu: per stage 32 KB arrive by TMA,
-            // 32 KB are read and 64 KB written by the split, 96 KB are read by the 12 MMAs).  Here
-            //  * the raw A tile arrives as two k-halves of [64 rows x 16 complex = 128 bytes],
-            //    SWIZZLE_128B, so that one thread per row reads 16-byte chunks without bank conflicts
-            //    (TMA cannot de-interleave: the traversal stride of dimension 0 is ignored and the other
-            //    strides must be multiples of 16 bytes);
-            //  * thread L of the transform warps reads raw row L % 64, keeps the real (L < 64) or the
-            //    imaginary parts, splits them and writes Ahi / Alo straight into tensor memory
-            //    (tcgen05.st, lane L = row L of A' = [Re; Im], one column per k);
-            //  * the MMAs take A from tensor memory ([a_tmem] operand) and only B from shared memory.
-            // Per stage: 32 KB by TMA, 48 KB read (A twice) and 32 KB written by the split, 48 KB read by
-            // the MMAs = 160 KB instead of 224 KB.
-            // TMEM: H[2], S as above (columns 0-383), A stage u: hi at 384 + 64 u, lo at 416 + 64 u.
-            namespace at {
-                constexpr int XRAW_STAGES = 4, XOP_STAGES = 2;
-                constexpr int XRAW_A = 128 * 128, XRAW_B = TN * BKC * 8; // 16 KB each
-                constexpr int XRAW_STAGE = XRAW_A + XRAW_B, XOP_STAGE = 2 * OP_TILE;
-                constexpr int XSMEM_DATA = XOP_STAGES * XOP_STAGE + XRAW_STAGES * XRAW_STAGE;
-                constexpr int XSMEM_BYTES = XSMEM_DATA + 1024 + 256;
-            }
-
-            __device__ __forceinline__ void mma_tf32_ts(unsigned d_tmem, unsigned a_tmem, unsigned long long bdesc,
-                                                        unsigned idesc, unsigned accumulate) {
-                asm volatile("{\n\t"
-                             ".reg .pred p;\n\t"
-                             "setp.ne.b32 p, %4, 0;\n\t"
-                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
-                             "}" ::"r"(d_tmem),
-                             "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                             : "memory");
-            }
-            __device__ __forceinline__ void tmem_st16(unsigned taddr, const float *v) {
-                asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-                             "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-                             "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
-                             "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]),
-                             "f"(v[15])
-                             : "memory");
-            }
-
-            __global__ void __launch_bounds__(THREADS, 1)
-                contract_tc_atmem_kernel(const __grid_constant__ CUtensorMap map_a,
-                                         const __grid_constant__ CUtensorMap map_b,
-                                         const __grid_constant__ Params p, float *__restrict__ ws) {
-                                extern __shared__ unsigned char smem_raw[];
-                unsigned char *smem = reinterpret_cast<unsigned char *>(
-                    (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-                unsigned char *ops = smem;                         // [at::XOP_STAGES][Bhi, Blo]
-                unsigned char *raw = smem + at::XOP_STAGES * at::XOP_STAGE;  // [at::XRAW_STAGES][A (de-interleaved), B]
-                unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem + at::XSMEM_DATA);
-                const unsigned bar0 = smem_u32(bars);
-                auto raw_full = [&](int s) { return bar0 + 8u * s; };
-                auto raw_empty = [&](int s) { return bar0 + 8u * (at::XRAW_STAGES + s); };
-                auto op_full = [&](int u) { return bar0 + 8u * (2 * at::XRAW_STAGES + u); };
-                auto op_empty = [&](int u) { return bar0 + 8u * (2 * at::XRAW_STAGES + at::XOP_STAGES + u); };
-                auto acc_full = [&](int b) { return bar0 + 8u * (2 * at::XRAW_STAGES + 2 * at::XOP_STAGES + b); };
-                auto acc_empty = [&](int b) { return bar0 + 8u * (2 * at::XRAW_STAGES + 2 * at::XOP_STAGES + 2 + b); };
-                unsigned *tmem_slot = reinterpret_cast<unsigned *>(bars + 2 * at::XRAW_STAGES + 2 * at::XOP_STAGES + 4);
-
-                const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-                long long bid = blockIdx.x;
-                const int nt = (int)(bid % p.ntiles);
-                bid /= p.ntiles;
-                const int mt = (int)(bid % p.mtiles);
-                bid /= p.mtiles;
-                const int ks = (int)(bid % p.ksplit);
-                const long long t = bid / p.ksplit;
-                const int t0 = (int)(t % p.tsize[0]), t1 = (int)(t / p.tsize[0]);
-                const int kstep0 = (int)((long long)p.ksteps * ks / p.ksplit);
-                const int kstep1 = (int)((long long)p.ksteps * (ks + 1) / p.ksplit);
-                const int nsteps = kstep1 - kstep0;
-
-                if (tid == 0) {
-                    for (int s = 0; s < at::XRAW_STAGES; ++s) mbar_init(raw_full(s), 1), mbar_init(raw_empty(s), 128);
-                    for (int u = 0; u < at::XOP_STAGES; ++u) mbar_init(op_full(u), 128), mbar_init(op_empty(u), 1);
-                    for (int b = 0; b < 2; ++b) mbar_init(acc_full(b), 1), mbar_init(acc_empty(b), 128);
-                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                }
-                if (warp == 9) {
-                    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                                     smem_u32(tmem_slot)),
-                                 "n"(TMEM_COLS)
-                                 : "memory");
-                    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-                }
-                if (warp == 8 && lane == 0) {
-                    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-                    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-                }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncthreads();
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const unsigned tmem = *tmem_slot;
-                const int P = p.promote > 0 ? p.promote : nsteps;
-                const int nchunks = (nsteps + P - 1) / P;
-
-                if (warp == 8) {
-                    // ===== TMA producer: A real parts, A imaginary parts (element stride 2), B raw =========
-                    if (lane == 0) {
-                        for (int it = 0; it < nsteps; ++it) {
-                            const int s = it % at::XRAW_STAGES;
-                            mbar_wait(raw_empty(s), ((it / at::XRAW_STAGES) & 1) ^ 1);
-                            mbar_expect_tx(raw_full(s), at::XRAW_STAGE);
-                            const int kc = (kstep0 + it) * (2 * BKC); // in floats
-                            const unsigned dst = smem_u32(raw + s * at::XRAW_STAGE);
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) // k-half h: 64 rows x 16 complex (128 bytes per row)
-                                tma_load_4d(dst + h * 8192, &map_a, kc + 32 * h, mt * TM, t0, t1, raw_full(s));
-                            tma_load_4d(dst + at::XRAW_A, &map_b, kc, nt * TN, t0, t1, raw_full(s));
-                        }
-                    }
-                } else if (warp == 9) {
-                    // ===== MMA issuer: A from tensor memory, B from shared memory ==========================
-                    if (lane == 0) {
-                        for (int it = 0; it < nsteps; ++it) {
-                            const int u = it % at::XOP_STAGES;
-                            const int c = it / P, b = c & 1;
-                            const bool first = it % P == 0, last = (it % P == P - 1) || it == nsteps - 1;
-                            mbar_wait(op_full(u), (it / at::XOP_STAGES) & 1);
-                            if (first) mbar_wait(acc_empty(b), ((c >> 1) & 1) ^ 1);
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const unsigned base = smem_u32(ops + u * at::XOP_STAGE);
-                            const unsigned long long bhi = op_desc(base), blo = op_desc(base + OP_TILE);
-                            const unsigned ahi = tmem + 384u + (unsigned)(u * 64), alo = ahi + 32u;
-                            const unsigned H = tmem + (unsigned)(b * 128), S = tmem + 256u;
-#pragma unroll
-                            for (int k4 = 0; k4 < BKC / 8; ++k4) {
-                                const unsigned long long adv = (unsigned long long)(k4 * 2);
-                                const unsigned ak = (unsigned)(k4 * 8);
-                                mma_tf32_ts(H, ahi + ak, bhi + adv, IDESC, !(first && k4 == 0));
-                                mma_tf32_ts(S, ahi + ak, blo + adv, IDESC, (it | k4) != 0);
-                                mma_tf32_ts(S, alo + ak, bhi + adv, IDESC, 1);
-                            }
-                            mma_commit(op_empty(u)); // frees the B tiles and the A columns of this stage
-                            if (last) mma_commit(acc_full(b));
-                        }
-                    }
-                } else if (warp >= 4) {
-                    // ===== accumulation warps (identical to the kernel above) ===============================
-                    const unsigned lane_base = (unsigned)((warp & 3) * 32) << 16;
-                    float sum[128];
-#pragma unroll
-                    for (int j = 0; j < 128; ++j) sum[j] = 0.f;
-                    for (int c = 0; c < nchunks; ++c) {
-                        const int b = c & 1;
-                        mbar_wait(acc_full(b), (c >> 1) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            unsigned v[32];
-                            tmem_ld32(tmem + lane_base + (unsigned)(b * 128 + q * 32), v);
-                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) sum[q * 32 + j] += __uint_as_float(v[j]);
-                        }
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        mbar_arrive(acc_empty(b));
-                    }
-                    const long long tile_id = ((t * p.mtiles + mt) * p.ntiles + nt) * (long long)p.ksplit + ks;
-                    float *out = ws + tile_id * (128 * 128) + ((warp & 3) * 32 + lane) * 128;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        unsigned v[32];
-                        tmem_ld32(tmem + lane_base + (unsigned)(256 + q * 32), v);
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4 *>(out + q * 32 + j * 4) =
-                                make_float4(sum[q * 32 + 4 * j] + __uint_as_float(v[4 * j]),
-                                            sum[q * 32 + 4 * j + 1] + __uint_as_float(v[4 * j + 1]),
-                                            sum[q * 32 + 4 * j + 2] + __uint_as_float(v[4 * j + 2]),
-                                            sum[q * 32 + 4 * j + 3] + __uint_as_float(v[4 * j + 3]));
-                    }
-                } else {
-                    // ===== transform warps (0-3): thread tid = row tid of A' (TMEM lane tid) ================
-                    const int g = tid & 7, swap = (g >> 2) & 1;
-                    const unsigned lane_base = (unsigned)(warp * 32) << 16;
-                    for (int it = 0; it < nsteps; ++it) {
-                        const int s = it % at::XRAW_STAGES, u = it % at::XOP_STAGES;
-                        mbar_wait(raw_full(s), (it / at::XRAW_STAGES) & 1);
-                        mbar_wait(op_empty(u), ((it / at::XOP_STAGES) & 1) ^ 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const unsigned ra = smem_u32(raw + s * at::XRAW_STAGE);
-                        // A: raw row tid % 64 of either k-half (128 bytes, chunk c stored at c ^ (row % 8));
-                        // threads 0-63 keep the real parts, 64-127 the imaginary parts
-                        const int row = tid & 63;
-                        const bool imag = tid >= 64;
-                        const unsigned arow = ra + (unsigned)row * 128u;
-                        const unsigned acol = tmem + lane_base + 384u + (unsigned)(u * 64);
-#pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            float x[16], h[16], l[16];
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                const float4 v = lds128(arow + (unsigned)(half * 8192) + (unsigned)((c ^ (row & 7)) << 4));
-                                x[2 * c] = imag ? v.y : v.x, x[2 * c + 1] = imag ? v.w : v.z;
-                            }
-#pragma unroll
-                            for (int q = 0; q < 16; ++q) h[q] = tf32_hi(x[q]), l[q] = tf32_hi(x[q] - h[q]);
-                            tmem_st16(acol + (unsigned)(half * 16), h);
-                            tmem_st16(acol + 32u + (unsigned)(half * 16), l);
-                        }
-                        // B: as in the kernel above (item = row r, group g of 4 complex)
-                        const unsigned src = ra + at::XRAW_A;
-                        const unsigned hi = smem_u32(ops + u * at::XOP_STAGE), lo = hi + OP_TILE;
-                        float4 f[4], hh[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int r = (tid >> 3) + 16 * i;
-                            const unsigned b = src + r * (BKC * 8) + g * 32;
-                            f[i] = lds128(b + swap * 16);
-                            hh[i] = lds128(b + 16 - swap * 16);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int r = (tid >> 3) + 16 * i;
-                            const unsigned off = (unsigned)((r >> 3) * 1024 + (r & 7) * 128 + ((g ^ (r & 7)) << 4));
-                            split_store(swap ? hh[i] : f[i], swap ? f[i] : hh[i], hi, lo, off);
-                        }
-                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        mbar_arrive(op_full(u));
-                        mbar_arrive(raw_empty(s));
-                    }
-                }
-
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncthreads();
-                if (warp == 9) {
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS)
-                                 : "memory");
-                }
-            }
 
             /// Sum the K slices (fixed order, double), combine the four real blocks, alpha, beta, strides
             __global__ void __launch_bounds__(256)
@@ -668,7 +448,7 @@ namespace sbb {
 
             /// The operand as a 4-d float tensor (2k, row, t0, t1); out-of-range rows and k read as zero
             CUtensorMap make_map(const void *base, long long K, int rows, long long row_stride, const Problem &p,
-                                 bool second, bool deinterleave /* half rows, swizzled */ = false) {
+                                 bool second) {
                 CUtensorMap m;
                 const cuuint64_t dims[4] = {(cuuint64_t)(2 * K), (cuuint64_t)rows,
                                             (cuuint64_t)(p.nT > 0 ? p.T[0].size : 1),
@@ -678,12 +458,10 @@ namespace sbb {
                 const cuuint64_t strides[3] = {(cuuint64_t)((rows > 1 ? row_stride : K) * 8),
                                                (cuuint64_t)((p.nT > 0 ? ts(0) : K) * 8),
                                                (cuuint64_t)((p.nT > 1 ? ts(1) : K) * 8)};
-                // half_rows: boxes of 16 complex per row (128 bytes) in the SWIZZLE_128B pattern
-                const cuuint32_t box[4] = {deinterleave ? 32u : 2u * BKC, (cuuint32_t)TM, 1, 1};
-                const cuuint32_t estr[4] = {1, 1, 1, 1};
+                const cuuint32_t box[4] = {2 * BKC, (cuuint32_t)TM, 1, 1}, estr[4] = {1, 1, 1, 1};
                 const CUresult r = encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims,
                                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                             deinterleave ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_SWIZZLE_NONE,
                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS)
                     throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
@@ -772,12 +550,7 @@ namespace sbb {
                 *describe = ss.str();
                 return;
             }
-            static int atmem = -1; // SBB_TC_ATMEM=1: A operand through tensor memory (variant under validation)
-            if (atmem < 0) {
-                const char *e = std::getenv("SBB_TC_ATMEM");
-                atmem = e ? std::atoi(e) : 0;
-            }
-            const CUtensorMap ma = make_map(v0, p.K, p.M, pr.M.s0, pr, false, atmem != 0);
+            const CUtensorMap ma = make_map(v0, p.K, p.M, pr.M.s0, pr, false);
             const CUtensorMap mb = make_map(v1, p.K, p.N, pr.N.s1, pr, true);
             float *ws = (float *)pool_alloc(device, (size_t)ctas * 128 * 128 * sizeof(float));
             static bool attr_set[64] = {false};
@@ -787,17 +560,7 @@ namespace sbb {
                            "cudaFuncSetAttribute");
                 attr_set[device] = true;
             }
-            if (atmem) {
-                static bool attr2[64] = {false};
-                if (!attr2[device]) {
-                    cuda_check(cudaFuncSetAttribute(contract_tc_atmem_kernel,
-                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, at::XSMEM_BYTES),
-                               "cudaFuncSetAttribute");
-                    attr2[device] = true;
-                }
-                KernelTimer timer("contract_tc", stream);
-                contract_tc_atmem_kernel<<<(unsigned)ctas, THREADS, at::XSMEM_BYTES, stream>>>(ma, mb, p, ws);
-            } else {
+            {
                 KernelTimer timer("contract_tc", stream);
                 contract_tc_kernel<<<(unsigned)ctas, THREADS, SMEM_BYTES, stream>>>(ma, mb, p, ws);
             }
