@@ -319,9 +319,10 @@ def local_copy(alpha, o0, from0, size0, dim0, v0, mask0, ctx0, o1, from1, dim1, 
 
 
 def copy_plan(elem_size1, p0, ncomponents0, o0, from0, size0, dim0, p1, ncomponents1, o1, from1,
-              dim1, nranks, rank, co, copyadd, alpha_is_zero=False):
+              dim1, nranks, rank, co, copyadd, alpha_is_zero=False, phases=None):
     """The list of strided-box operations `copy` would run on `rank` (host only, no GPU needed).
-    Returns (ops, wire) with ops = list of dicts, wire = {peer: (send_elems, recv_elems)}."""
+    Returns (ops, wire) with ops = list of dicts, wire = {peer: (send_elems, recv_elems)}; if
+    `phases` is a dict it receives {peer: phase of my message to that peer}."""
     n0, n1 = len(o0), len(o1)
     a = [_partition(p0, nranks * ncomponents0, n0), _ia(from0, n0), _ia(size0, n0), _ia(dim0, n0),
          _partition(p1, nranks * ncomponents1, n1), _ia(from1, n1), _ia(dim1, n1)]
@@ -345,6 +346,8 @@ def copy_plan(elem_size1, p0, ncomponents0, o0, from0, size0, dim0, p1, ncompone
             continue
         if w[0] == "wire":
             wire[int(w[2])] = (int(w[4]), int(w[6]))
+            if phases is not None and int(w[4]) > 0:
+                phases[int(w[2])] = int(w[8])
         elif w[0] == "op":
             i_size, i_ss, i_ds, i_rot = (w.index("size"), w.index("sstride"), w.index("dstride"),
                                          w.index("rot"))

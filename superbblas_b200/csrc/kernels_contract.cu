@@ -53,7 +53,6 @@ namespace sbb {
             int conj0, conj1;
             int bn; // columns of an output tile of the mma kernel
             int out_order[3]; // generic kernel: groups (0 = T, 1 = M, 2 = N) from fastest to slowest thread index
-            int debug; // experiments only (SBB_MMA_DEBUG): 1 = no global loads in the main loop, 2 = also no barrier, 4 = no fragment loads
             // mma kernel
             int mtiles, ntiles, ksplit, ksteps; // ksteps = ceil(K/BK)
             int a_sr, a_sk, b_sr, b_sk;         // shared-memory strides (elements) of the operand tiles
@@ -250,38 +249,6 @@ namespace sbb {
             asm volatile("cp.async.wait_group %0;" ::"n"(N));
         }
 
-        // ---- TMA bulk copies (cp.async.bulk, SASS UBLKCP) completing on an mbarrier ------------------
-        __device__ __forceinline__ unsigned smem_u32(const void *p) {
-            return (unsigned)__cvta_generic_to_shared(p);
-        }
-        __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-        }
-        __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                         "r"(bytes)
-                         : "memory");
-        }
-        __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-            asm volatile("{\n\t"
-                         ".reg .pred p;\n\t"
-                         "WAIT_%=:\n\t"
-                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                         "@p bra DONE_%=;\n\t"
-                         "bra WAIT_%=;\n\t"
-                         "DONE_%=:\n\t"
-                         "}" ::"r"(smem_u32(bar)),
-                         "r"(parity)
-                         : "memory");
-        }
-        __device__ __forceinline__ void bulk_load(void *dst, const void *src, unsigned bytes,
-                                                  unsigned long long *bar) {
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-                             "r"(smem_u32(dst)),
-                         "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                         : "memory");
-        }
-
         template <typename T> struct Frag; // fragment element as loaded from shared memory
         template <> struct Frag<double> {
             static constexpr bool cplx = false;
@@ -306,7 +273,7 @@ namespace sbb {
             return group_offset(K, k, stride);
         }
 
-        template <typename T, int BN, int BK, int STAGES, int MINB, bool BULK>
+        template <typename T, int BN, int BK, int STAGES, int MINB>
         __global__ void __launch_bounds__(MMA_THREADS, MINB)
             contract_mma_kernel(const __grid_constant__ ContractParams p, const T *__restrict__ v0,
                                 const T *__restrict__ v1, typename Acc<T>::type *__restrict__ ws) {
@@ -409,57 +376,6 @@ namespace sbb {
                 }
             };
 
-            // TMA variant of the loader (operands whose tile rows are contiguous in memory): one
-            // cp.async.bulk per tile row instead of one cp.async per element; completion is
-            // tracked by one mbarrier per stage.  k-contiguous operand: BM (BN) copies of BK elements;
-            // row-contiguous operand: BK copies of BM (BN) elements.
-            __shared__ __align__(8) unsigned long long full_bar[STAGES];
-            long long bulk_off = 0; // source offset (elements) of this thread's copy at k = 0
-            int bulk_dst = 0;       // shared-memory position (elements) of this thread's copy
-            unsigned bulk_bytes = 0;
-            long long bulk_kstride = 0;
-            const T *bulk_base = a_base;
-            if (BULK) {
-                if (tid == 0) {
-#pragma unroll
-                    for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
-                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-                }
-                __syncthreads();
-                const bool isA = tid < MMA_THREADS / 2;
-                const int c = isA ? tid : tid - MMA_THREADS / 2; // copy index inside the operand
-                const bool kfast = isA ? p.a_kfast : p.b_kfast;
-                const int rows = isA ? BM : BN;
-                const int ncopies = kfast ? rows : BK;
-                if (c < ncopies) {
-                    bulk_base = isA ? a_base : b_base;
-                    const long long kst = isA ? (p.K.n ? p.K.s0[0] : 0) : (p.K.n ? p.K.s1[0] : 0);
-                    if (kfast) {
-                        const long long r = min((long long)(isA ? mt * BM : nt * BN) + c,
-                                                (isA ? p.M.vol : p.N.vol) - 1);
-                        bulk_off = isA ? group_offset(p.M, r, p.M.s0) : group_offset(p.N, r, p.N.s1);
-                        bulk_dst = (isA ? 0 : a_stage) + c * (isA ? p.a_sr : p.b_sr);
-                        bulk_bytes = BK * sizeof(T);
-                        bulk_kstride = kst * BK; // per k-step
-                    } else {
-                        const long long r0 = (long long)(isA ? mt * BM : nt * BN);
-                        bulk_off = (isA ? group_offset(p.M, r0, p.M.s0) : group_offset(p.N, r0, p.N.s1)) +
-                                   c * kst;
-                        bulk_dst = (isA ? 0 : a_stage) + c * (isA ? p.a_sk : p.b_sk);
-                        bulk_bytes = rows * sizeof(T);
-                        bulk_kstride = kst * BK;
-                    }
-                }
-            }
-            auto load_stage_bulk = [&](int stage, int kstep) {
-                if (tid == 0)
-                    mbar_expect_tx(&full_bar[stage], (unsigned)((BM + BN) * BK * sizeof(T)));
-                if (bulk_bytes)
-                    bulk_load(smem + (size_t)stage * stage_elems + bulk_dst,
-                              bulk_base + bulk_off + (long long)kstep * bulk_kstride, bulk_bytes,
-                              &full_bar[stage]);
-            };
-
             // ---- accumulators: 4x4 blocks of 8x8 per warp ---------------------------------------------
             double acc[4][WN][ACC];
 #pragma unroll
@@ -482,16 +398,12 @@ namespace sbb {
             // ---- pipeline -----------------------------------------------------------------------------
 #pragma unroll
             for (int s = 0; s < STAGES - 1; ++s) {
-                if (s < nsteps) {
-                    if (BULK) load_stage_bulk(s, kstep0 + s);
-                    else load_stage(s, kstep0 + s);
-                }
-                if (!BULK) cp_async_commit();
+                if (s < nsteps) load_stage(s, kstep0 + s);
+                cp_async_commit();
             }
             for (int it = 0; it < nsteps; ++it) {
-                if (BULK) mbar_wait(&full_bar[it % STAGES], (unsigned)((it / STAGES) & 1));
-                else cp_async_wait<STAGES - 2>();
-                if (!(p.debug & 2)) __syncthreads();
+                cp_async_wait<STAGES - 2>();
+                __syncthreads();
                 const T *s = smem + (size_t)(it % STAGES) * stage_elems;
 #pragma unroll
                 for (int k4 = 0; k4 < BK / 4; ++k4) {
@@ -499,11 +411,8 @@ namespace sbb {
                         // the next stage's loads are issued in the shadow of the first block of DMMAs
                         // (the stage they overwrite was released by the barrier above)
                         const int nxt = it + STAGES - 1;
-                        if (nxt < nsteps && !(p.debug & 1)) {
-                            if (BULK) load_stage_bulk(nxt % STAGES, kstep0 + nxt);
-                            else load_stage(nxt % STAGES, kstep0 + nxt);
-                        }
-                        if (!BULK) cp_async_commit();
+                        if (nxt < nsteps) load_stage(nxt % STAGES, kstep0 + nxt);
+                        cp_async_commit();
                     }
                     if constexpr (CPLX) {
                         double ar[4], ai[4], nai[4], br[WN], bi[WN];
@@ -548,7 +457,7 @@ namespace sbb {
                     }
                 }
             }
-            if (!BULK) cp_async_wait<0>();
+            cp_async_wait<0>();
 
             // ---- partial tile to the workspace: ws[((t*mt*nt tile) * ksplit + ks)][m][n] -------------
             const long long tile_id = ((t * p.mtiles + mt) * p.ntiles + nt) * p.ksplit + ks;
@@ -711,16 +620,12 @@ namespace sbb {
             }
         }
 
-        template <typename T, int BN, int BK, int STAGES, int MINB, bool BULK>
+        template <typename T, int BN, int BK, int STAGES, int MINB>
         void launch_mma(ContractParams p, const double *alpha, const void *v0, const void *v1,
                         const double *beta, void *vr, int device, cudaStream_t stream,
                         std::string *describe) {
             using A = typename Acc<T>::type;
             p.bn = BN;
-            {
-                const char *e = std::getenv("SBB_MMA_DEBUG");
-                p.debug = e ? std::atoi(e) : 0;
-            }
             p.mtiles = (int)((p.M.vol + BM - 1) / BM);
             p.ntiles = (int)((p.N.vol + BN - 1) / BN);
             p.ksteps = (int)((p.K.vol + BK - 1) / BK);
@@ -755,7 +660,7 @@ namespace sbb {
                 ss << "mma f64" << (sizeof(A) != sizeof(T) ? " (float operands)" : "") << " tile=" << BM << "x" << BN << "x" << BK << " stages=" << STAGES
                    << " T=" << p.T.vol << " M=" << p.M.vol << " N=" << p.N.vol << " K=" << p.K.vol
                    << " ksplit=" << p.ksplit << " ctas=" << ctas << " smem=" << smem
-                   << " a_kfast=" << p.a_kfast << " b_kfast=" << p.b_kfast << " loader=" << (BULK ? "tma-bulk" : "cp.async");
+                   << " a_kfast=" << p.a_kfast << " b_kfast=" << p.b_kfast << " loader=cp.async";
                 *describe = ss.str();
                 return;
             }
@@ -763,14 +668,14 @@ namespace sbb {
             A *ws = (A *)pool_alloc(device, ws_bytes);
             static size_t attr_smem[64] = {0};
             if (smem > attr_smem[device]) {
-                cuda_check(cudaFuncSetAttribute(contract_mma_kernel<T, BN, BK, STAGES, MINB, BULK>,
+                cuda_check(cudaFuncSetAttribute(contract_mma_kernel<T, BN, BK, STAGES, MINB>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
                            "cudaFuncSetAttribute");
                 attr_smem[device] = smem;
             }
             {
                 KernelTimer timer("contract_mma", stream);
-                contract_mma_kernel<T, BN, BK, STAGES, MINB, BULK><<<(unsigned)ctas, MMA_THREADS, smem, stream>>>(
+                contract_mma_kernel<T, BN, BK, STAGES, MINB><<<(unsigned)ctas, MMA_THREADS, smem, stream>>>(
                     p, (const T *)v0, (const T *)v1, ws);
             }
             count_launch();
@@ -890,50 +795,9 @@ namespace sbb {
             return;
         }
         if (use_mma) {
-            // tile shape: 64x64 (2 CTAs/SM) or 64x32 (3 CTAs/SM, more warps to hide latencies);
-            // SBB_MMA_BN overrides for experiments
-            static int bn_env = -1;
-            if (bn_env < 0) {
-                const char *e = std::getenv("SBB_MMA_BN");
-                bn_env = e ? std::atoi(e) : 0;
-            }
-            const int bn = bn_env ? bn_env : 64;
-            static int bk_env = -1;
-            if (bk_env < 0) {
-                const char *e = std::getenv("SBB_MMA_BK");
-                bk_env = e ? std::atoi(e) : 0;
-            }
-            const int bk = bk_env ? bk_env : 8;
-            // TMA row loader when every tile row is one contiguous, 16-byte aligned run
-            const int esz = dtype_bytes(dtype);
-            auto rows_ok = [&](const Group &R, const long long *rs, const long long *ks, bool isA) {
-                const bool kfast = p.K.n > 0 && (R.n == 0 || ks[0] <= rs[0]);
-                if (kfast) return p.K.n == 1 && ks[0] == 1 && (8 * esz) % 16 == 0;
-                return R.n == 1 && rs[0] == 1 && R.vol % (isA ? BM : bn) == 0 && p.K.n <= 1;
-            };
-            static int bulk_env = -1;
-            if (bulk_env < 0) {
-                const char *e = std::getenv("SBB_MMA_BULK");
-                bulk_env = e ? std::atoi(e) : 0; // measured slower than per-element cp.async (27.6 vs 30.2 TFLOP/s): 128-byte bulk copies are too small
-            }
-            const bool bulk = bulk_env && f64 && !std::getenv("SBB_MMA_DEBUG") && bk == 8 && bn == 64 && p.K.vol % 8 == 0 &&
-                              rows_ok(p.M, p.M.s0, p.K.s0, true) && rows_ok(p.N, p.N.s1, p.K.s1, false) &&
-                              (uintptr_t)v0 % 16 == 0 && (uintptr_t)v1 % 16 == 0 &&
-                              [&] { // every other stride must keep 16-byte alignment too
-                                  if (esz == 16) return true;
-                                  for (const Group *g : {&p.T, &p.M, &p.N, &p.K})
-                                      for (int d = 0; d < g->n; ++d)
-                                          if ((g->s0[d] != 1 && g->s0[d] % 2) || (g->s1[d] != 1 && g->s1[d] % 2))
-                                              return false;
-                                  return true;
-                              }();
-#define SBB_MMA(T)                                                                                 \
-    do {                                                                                           \
-        if (bulk) launch_mma<T, 64, 8, 4, 2, true>(p, alpha, v0, v1, beta, vr, device, stream, describe); \
-        else if (bn == 32) launch_mma<T, 32, 8, 4, 3, false>(p, alpha, v0, v1, beta, vr, device, stream, describe);      \
-        else if (bk == 16) launch_mma<T, 64, 16, 2, 2, false>(p, alpha, v0, v1, beta, vr, device, stream, describe); \
-        else launch_mma<T, 64, 8, 4, 2, false>(p, alpha, v0, v1, beta, vr, device, stream, describe);      \
-    } while (0)
+            // 64x64 tile, BK = 8, 4 stages, 2 CTAs per SM (round 1 also measured 64x32 with 3 CTAs per SM,
+            // BK = 16 with 2 stages and a cp.async.bulk row loader: all slower, removed)
+#define SBB_MMA(T) launch_mma<T, 64, 8, 4, 2>(p, alpha, v0, v1, beta, vr, device, stream, describe)
             if (dtype == SBB_F64) SBB_MMA(double);
             else if (dtype == SBB_C128) SBB_MMA(double2);
             else if (dtype == SBB_F32) SBB_MMA(float);

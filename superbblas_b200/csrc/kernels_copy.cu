@@ -945,18 +945,8 @@ namespace sbb {
         /// Slots per thread of the raw-move kernels: 4- and 8-byte elements get 16 when the tile is
         /// transposed through shared memory (a tile must hold runs of >= 256 B on both sides and
         /// enough bytes in flight; measured +17 % for float, +7 % for 8-byte transposes), 8 otherwise
-        /// (the direct variant double-buffers in registers); SBB_EPT4 / SBB_EPT8 override (8 or 16)
-        int ept_for(int es) {
-            static int e4 = -1, e8 = -1;
-            if (e4 < 0) {
-                const char *a = std::getenv("SBB_EPT4"), *b = std::getenv("SBB_EPT8");
-                e4 = a ? std::atoi(a) : 16;
-                e8 = b ? std::atoi(b) : 16;
-            }
-            if (es == 4) return e4 == 8 ? 8 : 16;
-            if (es == 8) return e8 == 16 ? 16 : 8;
-            return EPT;
-        }
+        /// (the direct variant double-buffers in registers)
+        int ept_for(int es) { return es == 4 || es == 8 ? 16 : EPT; }
         int max_tile_for(int es) { return NT * ept_for(es); }
 
         /// Widen the element when the fastest dim is shared, contiguous and aligned

@@ -357,7 +357,7 @@ namespace sbb {
         for (int r = 0; r < nranks; ++r)
             if (send_elems[r] || recv_elems[r])
                 ss << "wire peer " << r << " send " << send_elems[r] << " recv " << recv_elems[r]
-                   << "\n";
+                   << " phase " << (send_elems[r] ? send_phase[r] : -1) << "\n";
         static const char *names[] = {"local", "pack", "unpack", "zero"};
         for (const auto &op : ops) {
             ss << "op " << names[op.kind] << " src " << op.src_part << " dst " << op.dst_part

@@ -139,3 +139,41 @@ def test_errors_match_reference_messages():
         sb.copy_plan(8, p, 1, "xy", [0, 0], [3, 2], [2, 2], p, 1, "xy", [0, 0], [2, 2], 1, 0, 1, 0)
     with pytest.raises(RuntimeError, match="wtf"):
         sb.copy_plan(8, p, 2, "xy", [0, 0], [2, 2], [2, 2], p, 1, "xy", [0, 0], [2, 2], 1, 0, 1, 0)
+
+
+def test_exchange_phases_are_a_proper_edge_colouring():
+    """Every message of an exchange gets a phase (CopyPlan::send_phase) computed identically on all
+    ranks; senders visit their receivers in phase order.  Proper: no two messages with the same
+    phase share a sender or a receiver.  And the property the ordering is for: a sender with a single
+    message owns phase 0 at its receiver (all senders start with their phase 0 at the same time)."""
+    rng = np.random.default_rng(5)
+    cases = []
+    for world in (4, 8):
+        dim = [4, 4, 4, 2 * world, 3]
+        pa = sb.basic_partitioning("xyztc", dim, [1, 1, 1, world, 1], "t", world, 1)
+        pb = sb.basic_partitioning("xyztc", dim, [1, 1, 2, world // 2, 1], "zt", world, 1)
+        cases.append((world, dict(p0=pa, o0="xyztc", from0=[0] * 5, size0=dim, dim0=dim, p1=pb, o1="xyztc",
+                                  from1=[0] * 5, dim1=dim, co=1, copyadd=0)))
+    for _ in range(20):
+        world = int(rng.integers(2, 7))
+        cases.append((world, C.random_copy_case(rng, nparts0=world, nparts1=world)))
+    for world, case in cases:
+        edges = {}
+        for rank in range(world):
+            ph = {}
+            _, wire = sb.copy_plan(8, case["p0"], 1, case["o0"], case["from0"], case["size0"], case["dim0"],
+                                   case["p1"], 1, case["o1"], case["from1"], case["dim1"], world, rank,
+                                   case["co"], case["copyadd"], phases=ph)
+            for peer, phase in ph.items():
+                assert peer != rank and wire[peer][0] > 0
+                edges[(rank, peer)] = phase
+        for (s0, r0), c0 in edges.items():
+            for (s1, r1), c1 in edges.items():
+                if (s0, r0) != (s1, r1) and c0 == c1:
+                    assert s0 != s1 and r0 != r1, (edges,)
+        outdeg = {s: sum(1 for e in edges if e[0] == s) for s in range(world)}
+        for (s, r), c in edges.items():
+            if outdeg[s] == 1 and all(outdeg[s2] >= 1 for (s2, r2) in edges if r2 == r):
+                single_to_r = [s2 for (s2, r2) in edges if r2 == r and outdeg[s2] == 1]
+                if len(single_to_r) == 1:
+                    assert c == 0, (edges, s, r)
