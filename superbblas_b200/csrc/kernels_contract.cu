@@ -393,7 +393,14 @@ namespace sbb {
 #pragma unroll
             for (int j = 0; j < WN; ++j)
                 b_frag[j] = a_stage + (wn * (BN / 2) + j * 8 + (lane >> 2)) * p.b_sr + (lane & 3) * p.b_sk;
-            const double sa = p.conj0 ? -1.0 : 1.0, sb = p.conj1 ? -1.0 : 1.0;
+            // conj and the minus of i*i are sign flips of the imaginary fragments.  They are done on
+            // the integer pipe (XOR of the sign bit): as FP64 multiplies / negations (8 per 64 DMMAs)
+            // they shared the FP64 pipe with the DMMAs and drew 23 % of the stall samples
+            // (profiles/r2_contract_mma_ncu.txt: DADD), with the tensor pipe at 88 %.
+            const unsigned sa = p.conj0 ? 0x80000000u : 0u, sb = p.conj1 ? 0x80000000u : 0u;
+            auto flip = [](double x, unsigned m) {
+                return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x));
+            };
 
             // ---- pipeline -----------------------------------------------------------------------------
 #pragma unroll
@@ -419,12 +426,12 @@ namespace sbb {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const double2 a = widen(s[a_frag[i] + k4 * 4 * p.a_sk]);
-                            ar[i] = a.x, ai[i] = sa * a.y, nai[i] = -ai[i];
+                            ar[i] = a.x, ai[i] = flip(a.y, sa), nai[i] = flip(a.y, sa ^ 0x80000000u);
                         }
 #pragma unroll
                         for (int j = 0; j < WN; ++j) {
                             const double2 b = widen(s[b_frag[j] + k4 * 4 * p.b_sk]);
-                            br[j] = b.x, bi[j] = sb * b.y;
+                            br[j] = b.x, bi[j] = flip(b.y, sb);
                         }
                         // four passes over the 16 blocks: the two DMMAs that accumulate into the
                         // same registers are 32 instructions apart, so none waits for the other

@@ -293,3 +293,42 @@ def test_errors(gu):
     sb.copy(1, p0, 1, "xy", [0, 0], [0, 0], [2, 2], [e], None, gpu, p, 1, "xy", [0, 0], [2, 2], [y],
             None, gpu, sb.FastToSlow, sb.Copy)
     sb.sync(gpu)
+
+
+def test_storage_staging_pattern(gu):
+    """The hot-path part of the reference's S3T save / load (storage.h:1029 local_save, :1149
+    local_load): a sub-box of a GPU tensor is permuted, scaled and converted (double -> float) on
+    the fly into a contiguous HOST buffer in the file's label order, and read back from the host
+    buffer into a sub-box of a GPU tensor.  Both directions against the oracle, bit for bit; the
+    save side also through a Request (the copy-back to the host completes at wait)."""
+    import torch
+    rng = np.random.default_rng(77)
+    gpu, cpu = sb.createGpuContext(0), sb.createCpuContext()
+    dim0 = [6, 5, 4, 3]                       # tensor "xyzn" on the GPU
+    from0, size0 = [1, 0, 2, 0], [4, 5, 2, 3]  # the sub-box that is saved (wraps in z)
+    o_file = "nzxy"
+    size1 = [size0["xyzn".index(c)] for c in o_file]
+    one = lambda d: np.array([[[0] * len(d), list(d)]], dtype=np.int32)  # noqa: E731
+    save = dict(alpha=0.5, p0=one(dim0), o0="xyzn", from0=from0, size0=size0, dim0=dim0, p1=one(size1),
+                o1=o_file, from1=[0] * 4, dim1=size1, co=0, copyadd=0, T=np.dtype(np.complex128),
+                Q=np.dtype(np.complex64))
+    v0, v1 = C.make_copy_data(save, 1)
+    want = C.oracle_copy(save, v0, v1)
+    src = torch.from_numpy(v0[0]).cuda()
+    host = v1[0].copy()
+    q = sb.copy(0.5, save["p0"], 1, "xyzn", from0, size0, dim0, [src], None, gpu, save["p1"], 1, o_file,
+                [0] * 4, size1, [host], None, cpu, sb.SlowToFast, sb.Copy, request=True)
+    q.wait()
+    assert C.bits_equal(host, want[0])
+    # load: the host buffer (file order) into a sub-box of another GPU tensor, converting back
+    load = dict(alpha=1, p0=one(size1), o0=o_file, from0=[0] * 4, size0=size1, dim0=size1, p1=one(dim0),
+                o1="xyzn", from1=from0, dim1=dim0, co=0, copyadd=0, T=np.dtype(np.complex64),
+                Q=np.dtype(np.complex128))
+    w0, w1 = C.make_copy_data(load, 2)
+    w0 = [host.copy()]
+    wantl = C.oracle_copy(load, w0, w1)
+    dst = torch.from_numpy(w1[0].copy()).cuda()
+    sb.copy(1, load["p0"], 1, o_file, [0] * 4, size1, size1, [w0[0]], None, cpu, load["p1"], 1, "xyzn", from0,
+            dim0, [dst], None, gpu, sb.SlowToFast, sb.Copy)
+    sb.sync(gpu)
+    assert C.bits_equal(dst.cpu().numpy(), wantl[0])

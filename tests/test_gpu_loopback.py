@@ -131,3 +131,71 @@ def test_deferred_request_with_host_destination(torch_cuda):
     q.wait()
     q.wait()  # a completed request can be waited on again
     assert C.bits_equal(dst, want[0])
+
+
+def test_halo_gather_with_requests_bsr_krylov_pattern(torch_cuda):
+    """The hot-path part of the reference's bsr_krylov (bsr.h:2189-2246): the input multi-vector,
+    partitioned on z,t, is gathered into halo-extended blocks in the operator's own label order with
+    a Request (reorder_tensor_request), the local operator runs, and the result is copied back.
+    Here: 8 loopback ranks, halo of width 1 in x,y,z,t with periodic wraparound, label permutation
+    "xyztsn" -> "nsxyzt"; the 'operator' is a nearest-neighbour sum evaluated with torch on every
+    rank's extended block; the result must equal the same stencil on the global field."""
+    torch = torch_cuda
+    world = 8
+    comms = sb.comm_create_local(world)
+    gpu = sb.createGpuContext(0)
+    try:
+        dim = [8, 8, 8, 8, 2, 3]                      # x y z t s n
+        procs = [1, 1, 2, 4, 1, 1]
+        px = sb.basic_partitioning("xyztsn", dim, procs, "zt", world, 1)
+        ext = sb.basic_partitioning(dim, procs, world, False, [1, 1, 1, 1, 0, 0])   # halo-extended boxes
+        perm = [dim[k] for k in (5, 4, 0, 1, 2, 3)]   # dims in "nsxyzt" order
+        ext_p = np.array([[[b[0][k] for k in (5, 4, 0, 1, 2, 3)], [b[1][k] for k in (5, 4, 0, 1, 2, 3)]]
+                          for b in ext], dtype=np.int32)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        glob = torch.randn(*reversed(dim), generator=g, device="cuda", dtype=torch.float64)  # [n,s,t,z,y,x]
+        one = np.array([[[0] * 6, dim]], dtype=np.int32)
+        # scatter the global field onto the ranks (single process source, no communicator needed per rank:
+        # every loopback rank takes its own block from the replicated global tensor)
+        x = []
+        for r in range(world):
+            f, s = px[r]
+            sl = tuple(slice(int(f[k]), int(f[k] + s[k])) for k in reversed(range(6)))
+            x.append(glob[sl].contiguous().view(-1))
+        # 1. halo gather with requests: "xyztsn" blocks -> extended "nsxyzt" blocks
+        xe = [torch.zeros(int(np.prod(ext_p[r][1])), device="cuda", dtype=torch.float64) for r in range(world)]
+        reqs = [sb.copy(1, px, 1, "xyztsn", [0] * 6, dim, dim, [x[r]], None, gpu, ext_p, 1, "nsxyzt", [0] * 6,
+                        perm, [xe[r]], None, gpu, sb.FastToSlow, sb.Copy, comm=comms[r], request=True)
+                for r in range(world)]
+        for q in reqs:
+            q.wait()
+        # 2. the local operator on every extended block: sum of the 8 neighbours in x,y,z,t (interior only)
+        ye = []
+        for r in range(world):
+            e = ext_p[r][1]                                       # extents in n s x y z t order
+            v = xe[r].view(*reversed([int(k) for k in e]))        # [t, z, y, x, s, n]
+            acc = torch.zeros_like(v)
+            for d in range(4):
+                acc += torch.roll(v, 1, dims=d) + torch.roll(v, -1, dims=d)
+            ye.append(acc[1:-1, 1:-1].contiguous().view(-1))      # interior in z,t (x,y are not split)
+        # 3. copy the result (the operator's own, non-overlapping output partition) back into the
+        #    caller's partition and order
+        px_p = np.array([[[b[0][k] for k in (5, 4, 0, 1, 2, 3)], [b[1][k] for k in (5, 4, 0, 1, 2, 3)]]
+                         for b in px], dtype=np.int32)
+        y = [torch.zeros_like(x[r]) for r in range(world)]
+        reqs = [sb.copy(1, px_p, 1, "nsxyzt", [0] * 6, perm, perm, [ye[r]], None, gpu, px, 1, "xyztsn", [0] * 6,
+                        dim, [y[r]], None, gpu, sb.FastToSlow, sb.Copy, comm=comms[r], request=True)
+                for r in range(world)]
+        for q in reqs:
+            q.wait()
+        sb.sync(gpu)
+        want = torch.zeros_like(glob)
+        for d in (2, 3, 4, 5):                                    # t z y x of [n,s,t,z,y,x]
+            want += torch.roll(glob, 1, dims=d) + torch.roll(glob, -1, dims=d)
+        for r in range(world):
+            f, s = px[r]
+            sl = tuple(slice(int(f[k]), int(f[k] + s[k])) for k in reversed(range(6)))
+            assert torch.equal(y[r], want[sl].contiguous().view(-1)), r
+    finally:
+        for c in comms:
+            c.destroy()
