@@ -41,7 +41,7 @@ sys.path.insert(0, ROOT)
 
 CPU_SAMPLE_T = 16               # time slices per part of the CPU sample (1/4 of one GPU's work)
 # the committed ncu digest the headline kernel's DRAM traffic is read from
-TRAFFIC_PROFILE = os.path.join("profiles", "r1_contract_mma_ncu_v2.txt")
+TRAFFIC_PROFILE = os.path.join("profiles", "r2_contract_mma_ncu.txt")
 
 
 def grid_for(n):

@@ -214,16 +214,48 @@ namespace sbb {
             }
         }
 
+        /// Second pass of the dot kernel: one WARP per output -- the lanes stride over the slices left
+        /// by the first pass and add their sums with a fixed shuffle tree (deterministic).  (One thread
+        /// per output walked the slices one dependent load after the other: 38 of the 40 us of an
+        /// m = n = 1, k = 49152, batch 32 call.)
         template <typename T>
         __global__ void __launch_bounds__(256)
             contract_dot_reduce_kernel(const __grid_constant__ dotk::DotParams p,
                                        const typename rowk::Acc<T>::type *__restrict__ ws, T *vr,
                                        typename rowk::Acc<T>::type alpha,
                                        typename rowk::Acc<T>::type beta) {
+            using A = typename rowk::Acc<T>::type;
+            constexpr int SB = dotk::SB;
             const long long total = dotk::outputs_of(p);
-            for (long long out = blockIdx.x * (long long)blockDim.x + threadIdx.x; out < total;
-                 out += (long long)gridDim.x * blockDim.x)
-                dotk::dot_reduce<T>(p, out, ws, vr, alpha, beta);
+            const int lane = threadIdx.x & 31, nsl = dotk::ws_slices(p);
+            const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+            for (long long out = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; out < total;
+                 out += nwarps) {
+                const int nn = (int)(out % p.n);
+                long long rem = out / p.n;
+                const int mm = (int)(rem % p.m);
+                long long t = rem / p.m;
+                const int pg = (mm / SB) * p.pgn + nn / SB;
+                const A *src = ws + ((t * (p.pgm * p.pgn) + pg) * (long long)nsl) * (SB * SB) +
+                               (mm % SB) * SB + nn % SB;
+                A acc;
+                rowk::set_zero(acc);
+                for (int s = lane; s < nsl; s += 32) acc = rowk::addc(acc, src[(long long)s * (SB * SB)]);
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc = rowk::addc(acc, shfl_down(acc, off));
+                if (lane == 0) {
+                    long long orr = p.moff_r[mm] + p.noff_r[nn];
+                    for (int d = 0; d < p.nd_t; ++d) {
+                        const long long c = t % p.size_t_[d];
+                        t /= p.size_t_[d];
+                        orr += c * p.sr_t[d];
+                    }
+                    A r = rowk::mulc(alpha, acc);
+                    T *w = vr + orr;
+                    if (!rowk::is_zero(beta)) r = rowk::addc(r, rowk::mulc(beta, rowk::widen(*w)));
+                    rowk::narrow(r, *w);
+                }
+            }
         }
 
         // ---- FP64 tensor-core kernel -----------------------------------------------------------------
@@ -591,9 +623,9 @@ namespace sbb {
                 dp, (const T *)v0, (const T *)v1, ws);
             count_launch();
             cuda_check(cudaGetLastError(), "contract_dot_partial_kernel launch");
-            const long long outs = dotk::outputs_of(dp);
+            const long long outs = dotk::outputs_of(dp); // one warp each
             const unsigned grid =
-                (unsigned)std::min<long long>((outs + 255) / 256, (long long)sm_count(device) * 8);
+                (unsigned)std::min<long long>((outs * 32 + 255) / 256, (long long)sm_count(device) * 8);
             contract_dot_reduce_kernel<T><<<grid, 256, 0, stream>>>(dp, ws, (T *)vr, scalar_of<A>(alpha),
                                                                   scalar_of<A>(beta));
             count_launch();
