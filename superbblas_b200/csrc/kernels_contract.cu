@@ -174,6 +174,70 @@ namespace sbb {
                 rowk::row_body<T>(p, row, va, vb, vr, alpha, beta);
         }
 
+        /// The same with the small operand staged in shared memory: when the 128 rows of a CTA share
+        /// one K x S block of it (`inner` = rows per block is a multiple of 128), the block is loaded
+        /// once per CTA and every product reads it with a broadcast LDS instead of a load through L1
+        /// (S x K loads per row: they, not the big operand, bound the kernel -- 49152 x 16 x 16
+        /// "update" shapes ran at 14 % of the HBM floor).
+        template <typename T>
+        __global__ void __launch_bounds__(128)
+            contract_row_smem_kernel(const __grid_constant__ rowk::RowParams p, const T *__restrict__ va,
+                                     const T *__restrict__ vb, T *vr, typename rowk::Acc<T>::type alpha,
+                                     typename rowk::Acc<T>::type beta) {
+            using A = typename rowk::Acc<T>::type;
+            using F = typename rowk::Fast<T>::type;
+            __shared__ F sb[rowk::KMAX * rowk::SMAX];
+            const long long nblocks = (p.rows + 127) / 128;
+            for (long long blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+                const long long row = blk * 128 + threadIdx.x;
+                // offsets of this row (the small operand's offset is the same for the whole CTA)
+                long long oa = 0, ob = 0, orr = 0, rem = row < p.rows ? row : p.rows - 1;
+#pragma unroll 1
+                for (int d = 0; d < p.nd; ++d) {
+                    const long long c = rem % p.size[d];
+                    rem /= p.size[d];
+                    oa += c * p.sa[d], ob += c * p.sb[d], orr += c * p.sr[d];
+                }
+                __syncthreads(); // the previous block's products are done with sb
+                for (int i = threadIdx.x; i < p.nk * p.ns; i += 128) {
+                    F b = vb[ob + p.koff_b[i / p.ns] + p.soff_b[i % p.ns]];
+                    if (p.conj_b) b = rowk::cj(b);
+                    sb[i] = b;
+                }
+                __syncthreads();
+                if (row >= p.rows) continue;
+                F acc[rowk::SMAX];
+#pragma unroll
+                for (int s = 0; s < rowk::SMAX; ++s) rowk::set_zero(acc[s]);
+                constexpr int KB = 8;
+                for (int k0 = 0; k0 < p.nk; k0 += KB) {
+                    F a[KB];
+#pragma unroll
+                    for (int j = 0; j < KB; ++j)
+                        if (k0 + j < p.nk) {
+                            a[j] = va[oa + p.koff_a[k0 + j]];
+                            if (p.conj_a) a[j] = rowk::cj(a[j]);
+                        }
+#pragma unroll
+                    for (int j = 0; j < KB; ++j)
+                        if (k0 + j < p.nk) {
+                            const F *bk = sb + (k0 + j) * p.ns;
+#pragma unroll
+                            for (int s = 0; s < rowk::SMAX; ++s)
+                                if (s < p.ns) rowk::fma_acc(acc[s], a[j], bk[s]);
+                        }
+                }
+#pragma unroll
+                for (int s = 0; s < rowk::SMAX; ++s)
+                    if (s < p.ns) {
+                        A r = rowk::mulc(alpha, rowk::widen(acc[s]));
+                        T *w = vr + orr + p.soff_r[s];
+                        if (!rowk::is_zero(beta)) r = rowk::addc(r, rowk::mulc(beta, rowk::widen(*w)));
+                        rowk::narrow(r, *w);
+                    }
+            }
+        }
+
         // ---- dot kernel (long contraction, both free groups small; bodies in contract_dot.hpp) -------
 
         __device__ __forceinline__ double shfl_down(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
@@ -198,11 +262,17 @@ namespace sbb {
             dotk::dot_partial_acc<T>(p, thread, va, vb, acc);
             __shared__ A part[dotk::CTA / 32][SB * SB];
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            // (only the live entries of the block: for m = n = 1 the 15 dead ones cost 300 shuffles
+            // per thread, most of the kernel; the condition is uniform over the CTA)
+            const int pgi = (int)((blockIdx.x / (p.slices / dotk::CTA)) % (p.pgm * p.pgn));
+            const int mlive = min(SB, p.m - (pgi / p.pgn) * SB), nlive = min(SB, p.n - (pgi % p.pgn) * SB);
 #pragma unroll
             for (int q = 0; q < SB * SB; ++q) {
                 A v = rowk::widen(acc[q / SB][q % SB]);
+                if (q / SB < mlive && q % SB < nlive) {
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v = rowk::addc(v, shfl_down(v, off));
+                    for (int off = 16; off > 0; off >>= 1) v = rowk::addc(v, shfl_down(v, off));
+                }
                 if (lane == 0) part[warp][q] = v;
             }
             __syncthreads();
@@ -606,9 +676,17 @@ namespace sbb {
             using A = typename Acc<T>::type;
             const unsigned grid =
                 (unsigned)std::min<long long>((rp.rows + 127) / 128, (long long)sm_count(device) * 12);
-            contract_row_kernel<T><<<grid, 128, 0, stream>>>(rp, (const T *)(swapped ? v1 : v0),
-                                                            (const T *)(swapped ? v0 : v1), (T *)vr,
-                                                            scalar_of<A>(alpha), scalar_of<A>(beta));
+            // rows that share one block of the small operand: the leading row dims it does not depend on
+            long long inner = 1;
+            for (int d = 0; d < rp.nd && rp.sb[d] == 0; ++d) inner *= rp.size[d];
+            if (inner % 128 == 0 && rp.ns * rp.nk >= 4)
+                contract_row_smem_kernel<T><<<grid, 128, 0, stream>>>(rp, (const T *)(swapped ? v1 : v0),
+                                                                     (const T *)(swapped ? v0 : v1), (T *)vr,
+                                                                     scalar_of<A>(alpha), scalar_of<A>(beta));
+            else
+                contract_row_kernel<T><<<grid, 128, 0, stream>>>(rp, (const T *)(swapped ? v1 : v0),
+                                                                (const T *)(swapped ? v0 : v1), (T *)vr,
+                                                                scalar_of<A>(alpha), scalar_of<A>(beta));
             count_launch();
             cuda_check(cudaGetLastError(), "contract_row_kernel launch");
         }
@@ -771,7 +849,8 @@ namespace sbb {
         // selects it for the accuracy comparison in the tests).
         if (dtype == SBB_C64 && (!force || std::strcmp(force, "tc") == 0) && p.K.n == 1 &&
             p.K.s0[0] == 1 && p.K.s1[0] == 1 && p.M.n <= 1 && p.N.n <= 1 && p.T.n <= 2 &&
-            p.K.vol >= 256 && p.M.vol >= 16 && p.N.vol >= 16 && p.M.vol < (1 << 30) && p.N.vol < (1 << 30)) {
+            p.K.vol >= 256 && p.M.vol >= 16 && p.N.vol >= 16 && p.M.vol * p.N.vol >= 512 &&
+            p.M.vol < (1 << 30) && p.N.vol < (1 << 30)) { // (16 x 16 and smaller: the dot kernel wastes less)
             tc::Problem tp;
             std::memset(&tp, 0, sizeof tp);
             tp.nT = p.T.n;

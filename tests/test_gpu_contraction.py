@@ -177,7 +177,7 @@ def test_skinny_shapes_of_the_reference_dist_program(gu, dtype):
     (20, 50, 1000, (3, 2), False, False, 0.5 - 2j, 1.5 + 0.5j),  # partial tiles, K tail, two batch dims
     (130, 70, 2048 + 8, (2,), False, True, -1, 0),      # several tiles per batch entry
     (64, 64, 4 * 32 * 37, (1,), True, True, 1, 1),      # no batch dim, long K (deep split-K)
-    (16, 16, 512, (5,), True, False, 2, 0),             # smallest eligible tile
+    (32, 16, 512, (5,), True, False, 2, 0),             # smallest eligible tile
 ])
 def test_tcgen05_complex_float(gu, shape):
     """Complex float contractions with a long contiguous K run on the tcgen05 path (TMA -> TF32 x 3
