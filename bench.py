@@ -377,17 +377,19 @@ def bench_contraction(E, W, steps, warmup, profile=True):
     sb = E.sb
     pv, pr, a, b, r = make_operands(E, W)
     fn = lambda: contraction_step(E, W, pv, pr, a, b, r, E.gpu)  # noqa: E731
-    sb.profile_enable(False)
-    sb.launch_count(reset=True)
-    ms = E.timed(fn, steps, warmup)
-    launches = sb.launch_count() * steps // (steps + warmup)  # the warm-up launches are counted too
+    # The dominant kernel is timed in the SAME steps as the step itself: a pair of CUDA events around
+    # every launch of it, on the stream it is launched on (two event records per 6 ms kernel do not
+    # change the step; a separate pass for the kernel timing saw other clocks than the timed pass)
+    sb.profile_enable(profile)
+
+    def reset_counters():  # after the warm-up steps: only the timed steps are counted
+        sb.profile_read("contract_mma")
+        sb.launch_count(reset=True)
+    ms = E.timed(fn, steps, warmup, after_warmup=reset_counters)
+    launches = sb.launch_count()
     out = {"ms_per_step": ms / steps, "value": W.flop * steps / (ms * 1e-3) / 1e12,
            "launches": launches}
     if profile:
-        # dominant kernel, timed with events on its own stream over another pass of the same steps
-        sb.profile_enable(True)
-        sb.profile_read("contract_mma")
-        E.timed(fn, steps, 1)
         kms, kn = sb.profile_read("contract_mma")
         sb.profile_enable(False)
         out["kernel_ms"] = E.max_over_ranks(kms / max(kn, 1))
@@ -451,10 +453,12 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, after_warmup=None):
         for _ in range(warmup):
             fn()
         barrier()
+        if after_warmup:
+            after_warmup()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with torch.cuda.stream(stream):
             e0.record()

@@ -12,5 +12,4 @@ print('strong4',d.get('strong_config4'))
 print({k:(round(v['ms'],3), round(v['GB/s']/d['n_gpus'])) for k,v in d['reshuffle'].items() if isinstance(v,dict) and 'ms' in v})
 "
 tail -5 gpurun_out/r2_bench_n$N.err
-if [ "$N" = "2" ]; then scripts/with_timeout.sh 120 scripts/micro/p2p_probe > gpurun_out/r2_p2p_probe.log 2>&1; echo "probe rc=$?"; cat gpurun_out/r2_p2p_probe.log; fi
 timeout 120 python scripts/tc_accuracy.py > gpurun_out/r2_tc_default.json 2>&1; cat gpurun_out/r2_tc_default.json | tail -1

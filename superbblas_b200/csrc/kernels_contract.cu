@@ -849,8 +849,7 @@ namespace sbb {
         // selects it for the accuracy comparison in the tests).
         if (dtype == SBB_C64 && (!force || std::strcmp(force, "tc") == 0) && p.K.n == 1 &&
             p.K.s0[0] == 1 && p.K.s1[0] == 1 && p.M.n <= 1 && p.N.n <= 1 && p.T.n <= 2 &&
-            p.K.vol >= 256 && p.M.vol >= 16 && p.N.vol >= 16 && p.M.vol * p.N.vol >= 512 &&
-            p.M.vol < (1 << 30) && p.N.vol < (1 << 30)) { // (16 x 16 and smaller: the dot kernel wastes less)
+            p.K.vol >= 256 && p.M.vol >= 16 && p.N.vol >= 16 && p.M.vol < (1 << 30) && p.N.vol < (1 << 30)) {
             tc::Problem tp;
             std::memset(&tp, 0, sizeof tp);
             tp.nT = p.T.n;
