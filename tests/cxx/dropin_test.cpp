@@ -204,6 +204,31 @@ int main() {
         cudaFree(d0), cudaFree(d1), cudaFree(dm0), cudaFree(dm1);
     }
 
+    // --- Request / wait (dist.h:54-61, :3554-3557): a permuting copy into a host destination is begun,
+    //     completed by wait(), and the request can be copied and waited on again ---------------------------
+    {
+        Coor<3> d0{5, 4, 3}, d1{3, 4, 5};
+        PartitionItem<3> p0{Coor<3>{}, d0}, p1{Coor<3>{}, d1};
+        std::vector<double> h0(60), h1(60, -1.0);
+        for (int i = 0; i < 60; ++i) h0[i] = i;
+        double *dsrc = to_device(h0);
+        const double *src = dsrc;
+        double *dst = h1.data();
+        Request req;
+        copy<3, 3>(2.0, &p0, 1, "abc", {}, d0, d0, &src, nullptr, &gpu, &p1, 1, "cba", {}, d1, &dst, nullptr,
+                   &cpu, FastToSlow, Copy, &req);
+        Request again = req;
+        wait(req);
+        wait(again);
+        int bad = 0;
+        for (int a = 0; a < 5; ++a)
+            for (int b = 0; b < 4; ++b)
+                for (int c = 0; c < 3; ++c)
+                    if (h1[c + 3 * (b + 4 * a)] != 2.0 * h0[a + 5 * (b + 4 * c)]) ++bad;
+        CHECK(bad == 0);
+        cudaFree(dsrc);
+    }
+
     // --- error behaviour ------------------------------------------------------------------------------------
     {
         Coor<2> d{2, 2};
