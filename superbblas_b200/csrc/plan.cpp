@@ -345,6 +345,7 @@ namespace sbb {
                 if (used_s[r].size() <= c) used_s[r].resize(c + 1, 0);
                 if (used_r[q].size() <= c) used_r[q].resize(c + 1, 0);
                 used_s[r][c] = used_r[q][c] = 1;
+                plan->nphases = std::max(plan->nphases, (int)c + 1);
                 if (r == me) plan->send_phase[q] = (int)c;
             }
         }

@@ -48,6 +48,7 @@ namespace sbb {
         /// (sender -> receiver pairs), computed identically on every rank, so that senders that
         /// visit their receivers in phase order do not meet at a receiver (index = peer rank)
         std::vector<int> send_phase;
+        int nphases = 0; ///< phases of the whole exchange (all ranks agree)
         std::string describe() const;
     };
 

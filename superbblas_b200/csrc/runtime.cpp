@@ -636,6 +636,7 @@ namespace sbb {
         int aux_grid = 0, nrounds = 0, evset = 0;
         unsigned long long seq0 = 0, exchange_id = 0;
         bool local_done = false, nothing_to_do = false;
+        std::vector<char> waited; ///< rounds whose wait kernel was already queued by begin() (pacing)
         std::vector<std::vector<int64_t>> rlo, rhi; // NCCL transport: receive windows per (round, peer)
 
         const CopyPlan &plan() const { return *plan_ptr; }
@@ -948,7 +949,27 @@ namespace sbb {
         seq0 = comm->seq;
         if (flags) comm->seq += (unsigned long long)nrounds;
         local_done = args.add; // additions keep plan order: everything after the last wait
+        // Pacing: nothing aligns the rounds of different senders in time.  A sender with fewer messages
+        // than the exchange has phases (a rank that keeps part of its data) would run ahead and meet
+        // the other sender of its receiver for half of the exchange (measured: the pack kernels alone
+        // of t-slabs -> (z,t) blocks take 6.0 ms on 4 and 8 GPUs where the busiest receiver's ingress
+        // allows 4.9).  Such a sender starts round k only when every rank has finished round k - 1
+        // (the flags it waits for anyway, one round earlier); balanced senders are not held back.
+        int my_peers = 0;
+        for (int r = 0; r < pl.nranks; ++r) my_peers += r != me && pl.send_elems[r] > 0;
+        const bool pace = flags && nrounds > 1 && my_peers > 0 && my_peers < pl.nphases;
+        waited.assign(nrounds, 0);
         for (int k = 0; k < nrounds; ++k) {
+            if (pace && k > 0) {
+                cuda_check(cudaStreamWaitEvent(h.comm_stream, comm_event(comm, evset, 2 * (k - 1), 2 * nrounds), 0),
+                           "cudaStreamWaitEvent");
+                launch_wait(comm->flags, comm->nranks, seq0 + k, h.comm_stream, wait_timeout_ns(), comm->error_dev);
+                cuda_check(cudaEventRecord(comm_event(comm, evset, 2 * (k - 1) + 1, 2 * nrounds), h.comm_stream),
+                           "cudaEventRecord");
+                cuda_check(cudaStreamWaitEvent(h.stream, comm_event(comm, evset, 2 * (k - 1) + 1, 2 * nrounds), 0),
+                           "cudaStreamWaitEvent");
+                waited[k - 1] = 1;
+            }
             set_grid_cap(pack_grid());
             // Order of the receivers inside a round: by the phase the planner gave every message (a
             // proper colouring of the sender -> receiver pairs, identical on all ranks).  With the
@@ -1023,7 +1044,9 @@ namespace sbb {
         auto wait_round = [&](int k) {
             use_device(home);
             cudaEvent_t arrived = comm_event(comm, evset, 2 * k + 1, 2 * nrounds);
-            if (flags) {
+            if (flags && waited[k]) {
+                // (already queued by begin(): the sender paced itself on this round)
+            } else if (flags) {
                 // every rank's stores of round k have landed in my arena once all flags reached the
                 // sequence number.  The one-warp wait kernel spins on the communication stream
                 cuda_check(cudaStreamWaitEvent(h.comm_stream, comm_event(comm, evset, 2 * k, 2 * nrounds), 0),
@@ -1038,7 +1061,7 @@ namespace sbb {
                                                    0),
                                "cudaStreamWaitEvent");
             }
-            cuda_check(cudaEventRecord(arrived, h.comm_stream), "cudaEventRecord");
+            if (!(flags && waited[k])) cuda_check(cudaEventRecord(arrived, h.comm_stream), "cudaEventRecord");
             for (int a : devs) {
                 use_device(a);
                 cuda_check(cudaStreamWaitEvent(stream_for(a), arrived, 0), "cudaStreamWaitEvent");
