@@ -8,7 +8,8 @@
 //
 // The body is written as a host/device function so that the indexing and the arithmetic are
 // checked on the CPU by tests/test_row_kernel_emulation.py (the same code runs one row per call);
-// only the launch itself needs a GPU.  Status: opt-in (SBB_ROW_KERNEL=1) until validated on a B200.
+// only the launch itself needs a GPU.  Validated on a B200 in round 2; default dispatch for these shapes
+// (kernels_contract.cu also has the variant that stages the small operand in shared memory).
 #pragma once
 #include "../../include/superbblas_b200.h"
 #include <cmath>
@@ -153,7 +154,7 @@ namespace sbb {
                 }
         }
 
-        // ---- output enumeration of the generic kernel (opt-in SBB_SIMT_ORDER=1) --------------------------
+        // ---- output enumeration of the generic kernel ---------------------------------------------------
         /// Thread index -> (t, m, n) with the groups listed in `order` (0 = T, 1 = M, 2 = N) from the
         /// fastest to the slowest; {2, 1, 0} is the kernel's default (n fastest, then m, then t)
         SBB_HD void output_index(const int *order, long long tvol, long long mvol, long long nvol,

@@ -21,9 +21,12 @@
 //  * contract_simt_kernel: any type, any shape; one thread per output element, K loop in registers,
 //    float types accumulate in double.  Used for short contractions (e.g. site-wise colour-spin
 //    contractions with M=N=1) and small tiles with many outputs.
-//  * opt-in until validated on a B200 (bodies checked on the CPU): contract_row_kernel
-//    (contract_row.hpp, short K and one small free group) and contract_dot_*_kernel
-//    (contract_dot.hpp, long K and two small free groups).
+//  * contract_row_kernel / contract_row_smem_kernel (contract_row.hpp: short K and one small free
+//    group; the small operand staged in shared memory when a CTA's rows share it) and
+//    contract_dot_*_kernel (contract_dot.hpp: long K and two small free groups; CTA tree + a warp per
+//    output in the second pass): the skinny shapes the reference hands to GEMV / dot calls
+//    (blas.h:686-699).  Bodies also run on the CPU (tests/test_row_kernel_emulation.py).
+//  * complex float with a long contiguous K goes to the tcgen05 kernel (kernels_contract_tc.cu).
 #include "contract_dot.hpp"
 #include "contract_row.hpp"
 #include "contract_tc.hpp"

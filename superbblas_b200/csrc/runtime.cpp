@@ -81,7 +81,6 @@ namespace sbb {
         constexpr int MAX_DEVICES = 64;
         DeviceState g_dev[MAX_DEVICES];
         bool g_peer[MAX_DEVICES][MAX_DEVICES];
-        std::mutex g_mutex;
     }
 
     void use_device(int device) { cuda_check(cudaSetDevice(device), "cudaSetDevice"); }

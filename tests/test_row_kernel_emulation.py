@@ -126,7 +126,7 @@ def test_row_kernel_body_against_numpy(emul, dtype):
 
 
 def test_output_enumeration_is_a_bijection_along_the_smallest_stride(emul):
-    """SBB_SIMT_ORDER=1: every output is visited exactly once and consecutive threads walk the group
+    """Output enumeration of the generic kernel: every output is visited exactly once and consecutive threads walk the group
     with the smallest result stride."""
     rng = np.random.default_rng(2200)
     emul.rowk_output_index.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_longlong, ctypes.c_longlong,
