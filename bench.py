@@ -270,7 +270,7 @@ class ClockSampler:
             self.path = f.name
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms",
-                 "100", "-i", str(self.index)], stdout=f, stderr=subprocess.DEVNULL)
+                 "50", "-i", str(self.index)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:  # noqa: BLE001
             self.proc = None
 

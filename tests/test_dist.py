@@ -10,13 +10,13 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def launch(n, backend, cases, port, timeout=600, stress=0):
+def launch(n, backend, cases, port, timeout=600, stress=0, extra_env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "dist_check.py"), "--backend", backend, "--cases", str(cases),
            "--stress", str(stress)]
     # tiny pipeline pieces so that the cutting of remote boxes is exercised by the small test cases
-    env = dict(os.environ, OMP_NUM_THREADS="1", SBB_CHUNK_BYTES="256")
+    env = dict(os.environ, OMP_NUM_THREADS="1", SBB_CHUNK_BYTES="256", **(extra_env or {}))
     # own session, so that a hang can be ended together with every worker process (a worker left
     # spinning on a GPU would disturb whatever runs next)
     proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env,
@@ -37,9 +37,14 @@ def test_gloo_world(n):
 
 
 @pytest.mark.gpu
-def test_nccl_world():
+@pytest.mark.parametrize("transport", ["peer-memory", "nccl-send-recv"])
+def test_nccl_world(transport):
+    """One process per GPU: random copies and contractions against the oracle and a stress run of
+    back-to-back exchanges, over the peer-memory transport (default) and over plain ncclSend/ncclRecv
+    (SBB_P2P=0, also the automatic fallback when the arenas cannot be mapped)."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
-    launch(min(n, 8), "nccl", 20, 29531, timeout=300, stress=300)
+    launch(min(n, 8), "nccl", 20, 29531 + (transport != "peer-memory"), timeout=300, stress=300,
+           extra_env={} if transport == "peer-memory" else {"SBB_P2P": "0"})
