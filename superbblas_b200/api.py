@@ -152,11 +152,44 @@ def _ip(a):
     return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
 
 
+_IV_CACHE = {}
+
+
+def _iv(x, n=None):
+    """A coordinate (or a flattened partition) as a ctypes int array.  Built directly from the Python
+    sequence (numpy's `.ctypes.data_as` costs ~5 us per argument, which dominated small calls) and
+    remembered by value: the arrays are only ever read, by us and by the library."""
+    key = x.tobytes() if isinstance(x, np.ndarray) and x.dtype == np.int32 else None
+    if key is None and type(x) in (list, tuple):
+        try:
+            key = tuple(x)
+            hash(key)
+        except TypeError:         # nested lists / arrays inside
+            key = None
+    c = _IV_CACHE.get(key) if key is not None else None
+    if c is None:
+        if not isinstance(x, np.ndarray):
+            try:
+                c = (ctypes.c_int * len(x))(*x)
+            except (TypeError, ValueError):   # nested or non-integer input: numpy flattens / rejects it
+                x = np.asarray(x)
+        if isinstance(x, np.ndarray):
+            a = np.ascontiguousarray(x, dtype=np.int32)
+            c = (ctypes.c_int * a.size).from_buffer_copy(a)
+        if key is not None:
+            if len(_IV_CACHE) >= 4096:
+                _IV_CACHE.clear()
+            _IV_CACHE[key] = c
+    if n is not None and len(c) != n:
+        raise RuntimeError("coordinate of the wrong length")
+    return c
+
+
 def _partition(p, nparts, nd):
     """int[nparts][2][nd]; a partition of the wrong length is the reference's "wtf" error
     (check_components, dist.h:709-716)."""
-    a = _ia(p)
-    if a.size != nparts * 2 * nd:
+    a = _iv(p)
+    if len(a) != nparts * 2 * nd:
         raise RuntimeError("wtf")
     return a
 
@@ -165,48 +198,62 @@ def _co(co):
     return {0: 0, 1: 1, "SlowToFast": 0, "FastToSlow": 1}[co]
 
 
+_TORCH = None      # (torch.Tensor, {torch dtype: code}), filled on first use: torch is optional here
+
+
+def _torch_types():
+    global _TORCH
+    if _TORCH is None:
+        import torch
+        _TORCH = (torch.Tensor, {torch.float32: F32, torch.float64: F64, torch.complex64: C64,
+                                 torch.complex128: C128, torch.int32: I32})
+    return _TORCH
+
+
 def _component(x):
-    """-> (pointer, dtype code, keepalive)"""
-    if isinstance(x, tuple):
-        return int(x[0]), int(x[1]), None
+    """-> (pointer, dtype code)"""
     if isinstance(x, np.ndarray):
-        if not x.flags["C_CONTIGUOUS"]:
+        if not x.flags.c_contiguous:
             raise RuntimeError("component arrays must be contiguous")
-        return (x.ctypes.data if x.size else 0), _NP2DT[x.dtype], x
-    import torch
-    if isinstance(x, torch.Tensor):
+        return (x.__array_interface__["data"][0] if x.size else 0), _NP2DT[x.dtype]
+    if isinstance(x, tuple):
+        return int(x[0]), int(x[1])
+    tensor, codes = _torch_types()
+    if isinstance(x, tensor):
         if not x.is_contiguous():
             raise RuntimeError("component tensors must be contiguous")
-        dt = {torch.float32: F32, torch.float64: F64, torch.complex64: C64,
-              torch.complex128: C128, torch.int32: I32}[x.dtype]
-        return (x.data_ptr() if x.numel() else 0), dt, x
+        return (x.data_ptr() if x.numel() else 0), codes[x.dtype]
     raise TypeError("unsupported component type %r" % type(x))
 
 
 def _components(v):
-    ptrs = (ctypes.c_void_p * max(len(v), 1))()
-    dts, keep = [], []
+    """-> (void*[ncomponents], dtype code, keepalive)"""
+    n = len(v)
+    if n == 1:
+        p, dt = _component(v[0])
+        return (ctypes.c_void_p * 1)(p or None), dt, v
+    ptrs = (ctypes.c_void_p * max(n, 1))()
+    dts = set()
     for i, x in enumerate(v):
-        p, dt, k = _component(x)
+        p, dt = _component(x)
         ptrs[i] = p or None
-        dts.append(dt)
-        keep.append(k)
-    if len(set(dts)) > 1:
+        dts.add(dt)
+    if len(dts) > 1:
         raise RuntimeError("components of a tensor must share one element type")
-    return ptrs, (dts[0] if dts else F64), keep
+    return ptrs, (dts.pop() if dts else F64), v
 
 
 def _contexts(ctx, n):
     if isinstance(ctx, Context):
         ctx = [ctx] * n
-    arr = (Context * max(n, 1))()
-    for i in range(n):
-        arr[i] = ctx[i]
-    return arr
+    if n == 0:
+        return (Context * 1)()
+    return (Context * n)(*ctx[:n])
 
 
 def _scalar(x):
-    return (ctypes.c_double * 2)(float(np.real(x)), float(np.imag(x)))
+    x = complex(x)
+    return (ctypes.c_double * 2)(x.real, x.imag)
 
 
 def _order(o):
@@ -294,11 +341,11 @@ def copy(alpha, p0, ncomponents0, o0, from0, size0, dim0, v0, mask0, ctx0,
         if mdt != F32:
             raise RuntimeError("masks must be float32 (MaskType)")
     nr = comm.nranks if comm else 1
-    a = [_partition(p0, nr * ncomponents0, n0), _ia(from0, n0), _ia(size0, n0), _ia(dim0, n0),
-         _partition(p1, nr * ncomponents1, n1), _ia(from1, n1), _ia(dim1, n1)]
-    call = (dt0, dt1, _scalar(alpha), n0, _ip(a[0]), ncomponents0, _order(o0),
-            _ip(a[1]), _ip(a[2]), _ip(a[3]), pv0, pm0, _contexts(ctx0, ncomponents0),
-            n1, _ip(a[4]), ncomponents1, _order(o1), _ip(a[5]), _ip(a[6]), pv1, pm1,
+    a = [_partition(p0, nr * ncomponents0, n0), _iv(from0, n0), _iv(size0, n0), _iv(dim0, n0),
+         _partition(p1, nr * ncomponents1, n1), _iv(from1, n1), _iv(dim1, n1)]
+    call = (dt0, dt1, _scalar(alpha), n0, a[0], ncomponents0, _order(o0),
+            a[1], a[2], a[3], pv0, pm0, _contexts(ctx0, ncomponents0),
+            n1, a[4], ncomponents1, _order(o1), a[5], a[6], pv1, pm1,
             _contexts(ctx1, ncomponents1), comm.handle if comm else None, _co(co), int(copyadd))
     if not request:
         check(lib().sbb_copy(*call))
@@ -324,15 +371,15 @@ def copy_plan(elem_size1, p0, ncomponents0, o0, from0, size0, dim0, p1, ncompone
     Returns (ops, wire) with ops = list of dicts, wire = {peer: (send_elems, recv_elems)}; if
     `phases` is a dict it receives {peer: phase of my message to that peer}."""
     n0, n1 = len(o0), len(o1)
-    a = [_partition(p0, nranks * ncomponents0, n0), _ia(from0, n0), _ia(size0, n0), _ia(dim0, n0),
-         _partition(p1, nranks * ncomponents1, n1), _ia(from1, n1), _ia(dim1, n1)]
+    a = [_partition(p0, nranks * ncomponents0, n0), _iv(from0, n0), _iv(size0, n0), _iv(dim0, n0),
+         _partition(p1, nranks * ncomponents1, n1), _iv(from1, n1), _iv(dim1, n1)]
     size = 1 << 16
     while True:
         buf = ctypes.create_string_buffer(size)
         needed = ctypes.c_size_t(0)
         rc = lib().sbb_copy_plan_describe(
-            elem_size1, n0, _ip(a[0]), ncomponents0, _order(o0), _ip(a[1]), _ip(a[2]), _ip(a[3]),
-            n1, _ip(a[4]), ncomponents1, _order(o1), _ip(a[5]), _ip(a[6]), nranks, rank, _co(co),
+            elem_size1, n0, a[0], ncomponents0, _order(o0), a[1], a[2], a[3],
+            n1, a[4], ncomponents1, _order(o1), a[5], a[6], nranks, rank, _co(co),
             int(copyadd), int(alpha_is_zero), buf, ctypes.c_size_t(size), ctypes.byref(needed))
         if rc == 2:
             size = needed.value + 16
@@ -374,15 +421,15 @@ def contraction(alpha, p0, from0, size0, dim0, ncomponents0, o0, conj0, v0, ctx0
     if dt0 == I32:
         raise RuntimeError("contraction: unsupported type")
     R = comm.nranks if comm else 1
-    a = [_partition(p0, R * ncomponents0, n0), _ia(from0, n0), _ia(size0, n0), _ia(dim0, n0),
-         _partition(p1, R * ncomponents1, n1), _ia(from1, n1), _ia(size1, n1), _ia(dim1, n1),
-         _partition(pr, R * ncomponentsr, nr), _ia(fromr, nr), _ia(sizer, nr), _ia(dimr, nr)]
+    a = [_partition(p0, R * ncomponents0, n0), _iv(from0, n0), _iv(size0, n0), _iv(dim0, n0),
+         _partition(p1, R * ncomponents1, n1), _iv(from1, n1), _iv(size1, n1), _iv(dim1, n1),
+         _partition(pr, R * ncomponentsr, nr), _iv(fromr, nr), _iv(sizer, nr), _iv(dimr, nr)]
     check(lib().sbb_contraction(
-        dt0, _scalar(alpha), n0, _ip(a[0]), _ip(a[1]), _ip(a[2]), _ip(a[3]), ncomponents0,
-        _order(o0), int(bool(conj0)), pv0, _contexts(ctx0, ncomponents0), n1, _ip(a[4]), _ip(a[5]),
-        _ip(a[6]), _ip(a[7]), ncomponents1, _order(o1), int(bool(conj1)), pv1,
-        _contexts(ctx1, ncomponents1), _scalar(beta), nr, _ip(a[8]), _ip(a[9]), _ip(a[10]),
-        _ip(a[11]), ncomponentsr, _order(o_r), pvr, _contexts(ctxr, ncomponentsr),
+        dt0, _scalar(alpha), n0, a[0], a[1], a[2], a[3], ncomponents0,
+        _order(o0), int(bool(conj0)), pv0, _contexts(ctx0, ncomponents0), n1, a[4], a[5],
+        a[6], a[7], ncomponents1, _order(o1), int(bool(conj1)), pv1,
+        _contexts(ctx1, ncomponents1), _scalar(beta), nr, a[8], a[9], a[10],
+        a[11], ncomponentsr, _order(o_r), pvr, _contexts(ctxr, ncomponentsr),
         comm.handle if comm else None, _co(co)))
 
 
@@ -415,8 +462,8 @@ def box_desc(size, sstride, dstride, soff=0, doff=0, rot=0):
 
 
 def permute_copy(desc, src, dst, alpha=1, add=False, device=0):
-    ps, dts, _ = _component(src) if src is not None else (0, None, None)
-    pd, dtd, _ = _component(dst)
+    ps, dts = _component(src) if src is not None else (0, None)
+    pd, dtd = _component(dst)
     if dts is None:
         dts = dtd
     check(lib().sbk_permute_copy(ctypes.byref(desc), ctypes.c_void_p(ps), dts, ctypes.c_void_p(pd),
