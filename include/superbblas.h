@@ -396,7 +396,7 @@ namespace superbblas {
         }
     }
 
-    // Diagnostics of the reference that callers and its tests reference; cheap no-ops here
+    // Diagnostics of the reference that callers and its tests reference
     /// SB_DEBUG (runtime_features.h:31): 0 = none; >= 2 makes every copy verify itself on
     /// index-valued mock tensors first (dist.h:2282-2285), which the library does in sbb_copy
     inline int getDebugLevel() {
@@ -406,10 +406,67 @@ namespace superbblas {
         }();
         return level;
     }
-    inline void resetTimings() {}
-    template <typename OStream> void reportTimings(OStream &) {}
-    template <typename OStream> void reportCacheUsage(OStream &) {}
-    template <typename OStream> void checkForMemoryLeaks(OStream &) {}
+    /// SB_TRACK_TIME / SB_TRACK_MEMORY (runtime_features.h): nonzero turns the reports below on
+    inline bool getTrackingTime() {
+        static bool on = [] {
+            const char *e = std::getenv("SB_TRACK_TIME");
+            return e && std::atoi(e) != 0;
+        }();
+        return on;
+    }
+    inline bool getTrackingMemory() {
+        static bool on = [] {
+            const char *e = std::getenv("SB_TRACK_MEMORY");
+            return e && std::atoi(e) != 0;
+        }();
+        return on;
+    }
+    namespace detail {
+        /// Text of one of the library's reports (sbb_report)
+        inline std::string report_text(int what) {
+            std::string buf(1 << 14, '\0');
+            for (;;) {
+                std::size_t needed = 0;
+                const int rc = sbb_report(what, &buf[0], buf.size(), &needed);
+                if (rc == 2) {
+                    buf.assign(needed + 16, '\0');
+                    continue;
+                }
+                if (rc != 0) throw std::runtime_error(sbb_last_error());
+                buf.resize(std::strlen(buf.c_str()));
+                return buf;
+            }
+        }
+    }
+    /// performance.h:357: forget what has been tracked so far
+    inline void resetTimings() {
+        if (sbb_reset_timings() != 0) throw std::runtime_error(sbb_last_error());
+    }
+    /// performance.h:365: per public call, host and device time, calls, flops and bytes (SB_TRACK_TIME)
+    template <typename OStream> void reportTimings(OStream &s) {
+        if (!getTrackingTime()) return;
+        s << detail::report_text(0);
+    }
+    /// performance.h:443: cached plans and pooled workspaces (SB_TRACK_MEMORY)
+    template <typename OStream> void reportCacheUsage(OStream &s) {
+        if (!getTrackingMemory()) return;
+        s << detail::report_text(1);
+    }
+    /// performance.h:476
+    template <typename OStream> void reportCurrentMemoryAllocations(OStream &s) {
+        if (!getTrackingMemory()) return;
+        s << detail::report_text(2);
+    }
+    /// performance.h:494: after clearCaches() nothing handed out by the library's allocator
+    /// (detail::vector, allocate) may still be around (SB_TRACK_MEMORY)
+    template <typename OStream> void checkForMemoryLeaks(OStream &s) {
+        if (!getTrackingMemory()) return;
+        long long blocks = 0, bytes = 0;
+        if (sbb_live_allocations(&blocks, &bytes) != 0) throw std::runtime_error(sbb_last_error());
+        if (blocks == 0) return;
+        reportCurrentMemoryAllocations(s);
+        throw std::runtime_error("checkForMemoryLeaks: some allocations are still around");
+    }
 
     // ---- partitions ---------------------------------------------------------------------------------
 

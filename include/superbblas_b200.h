@@ -82,6 +82,22 @@ int sbb_memcpy(void *dst, const sbb_context *dst_ctx, const void *src, const sbb
 int sbb_profile_enable(int on);
 int sbb_profile_read(const char *kernel, double *total_ms, long long *count);
 
+/* Reports of the public calls (performance.h:357-518).  With tracking on -- the environment variable
+ * SB_TRACK_TIME set to a nonzero number, or sbb_track_time(1) -- sbb_copy, sbb_copy_begin,
+ * sbb_request_wait and sbb_contraction accumulate per name: host seconds, device seconds (CUDA events
+ * on the library stream around the call, resolved when the report is read), calls, flops and bytes
+ * in the reference's units (tensor.h:1087-1088, :1593).  sbb_report writes text into buf:
+ *   what = 0  reportTimings: "name : S s (gpu_time: S calls: N flops: F bytes: B GFLOPs_single: ..
+ *             GBYTES/s: .. intensity: .. )", one line per name, alphabetically (empty when tracking is off)
+ *   what = 1  reportCacheUsage: cached plans, workspace pool per device
+ *   what = 2  reportCurrentMemoryAllocations: the pool blocks handed out and not returned
+ * It returns 2 and sets *needed when buf is too small.  sbb_live_allocations is what
+ * checkForMemoryLeaks (performance.h:494) looks at after clearCaches(). */
+int sbb_track_time(int on);
+int sbb_reset_timings(void);
+int sbb_report(int what, char *buf, size_t buflen, size_t *needed);
+int sbb_live_allocations(long long *blocks, long long *bytes);
+
 /* ---- communicator (NCCL over NVLink) ------------------------------------------------------------ */
 
 /* Write a 128-byte NCCL unique id (rank 0 calls it and broadcasts the bytes by any means) */

@@ -87,6 +87,58 @@ def profile_read(kernel):
     return ms.value, n.value
 
 
+def trackTime(on=True):
+    """What the environment variable SB_TRACK_TIME does in the reference (runtime_features.h)."""
+    check(lib().sbb_track_time(int(on)))
+
+
+def resetTimings():
+    check(lib().sbb_reset_timings())
+
+
+def _report(what):
+    size = 1 << 14
+    while True:
+        buf = ctypes.create_string_buffer(size)
+        needed = ctypes.c_size_t(0)
+        rc = lib().sbb_report(what, buf, ctypes.c_size_t(size), ctypes.byref(needed))
+        if rc == 2:
+            size = needed.value + 16
+            continue
+        check(rc)
+        return buf.value.decode()
+
+
+def reportTimings():
+    """reportTimings (performance.h:365) as text; empty unless tracking is on."""
+    return _report(0)
+
+
+def reportCacheUsage():
+    """reportCacheUsage (performance.h:443) as text."""
+    return _report(1)
+
+
+def timings():
+    """The timing report as {name: {cpu_time, gpu_time, calls, flops, bytes}}."""
+    out = {}
+    for line in reportTimings().splitlines()[2:]:
+        name, rest = line.split(" : ", 1)
+        w = rest.replace("(", " ").replace(")", " ").split()
+        out[name] = dict(cpu_time=float(w[0]), gpu_time=float(w[w.index("gpu_time:") + 1]),
+                         calls=int(w[w.index("calls:") + 1]), flops=float(w[w.index("flops:") + 1]),
+                         bytes=float(w[w.index("bytes:") + 1]))
+    return out
+
+
+def liveAllocations():
+    """-> (blocks, bytes) handed out by the library's allocator and not returned; what
+    checkForMemoryLeaks (performance.h:494) looks at."""
+    n, b = ctypes.c_longlong(0), ctypes.c_longlong(0)
+    check(lib().sbb_live_allocations(ctypes.byref(n), ctypes.byref(b)))
+    return n.value, b.value
+
+
 # --- communicator -------------------------------------------------------------------------------
 
 class Comm:

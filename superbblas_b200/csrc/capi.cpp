@@ -1,8 +1,11 @@
 // extern "C" entry points (include/superbblas_b200.h). Nothing here throws across the boundary.
 #include "contract_plan.hpp"
 #include "runtime.hpp"
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 
@@ -80,6 +83,188 @@ namespace {
     bool is_zero(int dtype, const double *a) {
         const bool cplx = dtype == SBB_C64 || dtype == SBB_C128;
         return a[0] == 0 && (!cplx || a[1] == 0);
+    }
+
+    // ---- SB_TRACK_TIME: what the public calls cost (reference: performance.h:357-441) -------------
+    struct Timing {
+        double cpu_s = 0, gpu_s = 0, flops = 0, bytes = 0;
+        long long calls = 0;
+    };
+    struct Interval { ///< device time of one call, not yet read back
+        std::string name;
+        int device;
+        cudaEvent_t start, stop;
+    };
+    std::map<std::string, Timing> g_timings;
+    std::vector<Interval> g_open;
+    std::map<int, std::vector<cudaEvent_t>> g_spare_events;
+    int g_track_time = -1;
+
+    bool track_time() {
+        if (g_track_time < 0) {
+            const char *e = std::getenv("SB_TRACK_TIME");
+            g_track_time = e && std::atoi(e) != 0;
+        }
+        return g_track_time != 0;
+    }
+
+    double now_s() {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+    }
+
+    cudaEvent_t timing_event(int device) {
+        auto &spare = g_spare_events[device];
+        if (!spare.empty()) {
+            cudaEvent_t e = spare.back();
+            spare.pop_back();
+            return e;
+        }
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return e;
+    }
+
+    /// Read the device times of the finished calls back (waits for them)
+    void resolve_intervals() {
+        for (Interval &i : g_open) {
+            float ms = 0;
+            cudaSetDevice(i.device);
+            if (cudaEventSynchronize(i.stop) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, i.start, i.stop) == cudaSuccess)
+                g_timings[i.name].gpu_s += ms * 1e-3;
+            else
+                cudaGetLastError();
+            g_spare_events[i.device].push_back(i.start);
+            g_spare_events[i.device].push_back(i.stop);
+        }
+        g_open.clear();
+    }
+
+    /// The device whose library stream brackets a call: the communicator's, else the first GPU
+    /// component (destination first, as the executors choose their home device), else the staging
+    /// device of an all-host call
+    int tracked_device(Comm *c, std::initializer_list<std::pair<const sbb_context *, int>> tensors) {
+        if (c) return c->device;
+        for (const auto &t : tensors)
+            for (int i = 0; t.first && i < t.second; ++i)
+                if (t.first[i].plat == SBB_CUDA) return t.first[i].device;
+        return default_device(nullptr);
+    }
+
+    /// One tracked public call; does nothing when tracking is off
+    struct Tracker {
+        const char *name;
+        bool on;
+        int device = -1;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t start = nullptr, stop = nullptr;
+        double t0 = 0;
+        WorkCounters w0;
+        template <typename PickDevice> Tracker(const char *name_, PickDevice pick) : name(name_), on(track_time()) {
+            if (!on) return;
+            w0 = work_counters();
+            try {
+                device = pick();
+                if (device >= 0) {
+                    stream = device_state(device).stream;
+                    use_device(device);
+                    start = timing_event(device), stop = timing_event(device);
+                    if (!start || !stop || cudaEventRecord(start, stream) != cudaSuccess) {
+                        cudaGetLastError();
+                        start = stop = nullptr;
+                    }
+                }
+            } catch (...) { // no usable device: the call itself will say so; host time is still counted
+                start = stop = nullptr;
+            }
+            t0 = now_s();
+        }
+        ~Tracker() {
+            if (!on) return;
+            Timing &t = g_timings[name];
+            t.cpu_s += now_s() - t0;
+            t.calls += 1;
+            t.flops += work_counters().flops - w0.flops;
+            t.bytes += work_counters().bytes - w0.bytes;
+            if (start && stop) {
+                cudaSetDevice(device);
+                if (cudaEventRecord(stop, stream) == cudaSuccess)
+                    g_open.push_back(Interval{name, device, start, stop});
+                else
+                    cudaGetLastError();
+                if (g_open.size() >= 1024) resolve_intervals(); // bounded: tracking is a diagnostic mode
+            }
+        }
+    };
+
+    std::string timings_report() {
+        if (!track_time()) return std::string();
+        resolve_intervals();
+        std::string s = "Timing of superbblas kernels:\n-----------------------------\n";
+        char line[512];
+        for (const auto &it : g_timings) { // std::map: alphabetical, like the reference's report
+            const Timing &t = it.second;
+            const double time = t.gpu_s > 0 ? t.gpu_s : t.cpu_s;
+            const double gflops = time > 0 ? t.flops / time / 1e9 : 0;
+            const double gbytes = time > 0 ? t.bytes / time / (1024.0 * 1024.0 * 1024.0) : 0;
+            const double intensity = t.bytes > 0 ? t.flops / (t.bytes / sizeof(float)) : 0;
+            std::snprintf(line, sizeof line,
+                          "%s : %.6f s (gpu_time: %.6f calls: %lld flops: %.0f bytes: %.0f GFLOPs_single: %.3e "
+                          "GBYTES/s: %.3e intensity: %.1f )\n",
+                          it.first.c_str(), t.cpu_s, t.gpu_s, t.calls, t.flops, t.bytes, gflops, gbytes,
+                          intensity);
+            s += line;
+        }
+        return s;
+    }
+
+    std::string cache_report() {
+        std::string s = "Cache usage of superbblas kernels:\n-----------------------------\n";
+        char line[256];
+        std::snprintf(line, sizeof line, "copy plans : %zu entries\n", plan_cache_size());
+        s += line;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess) cudaGetLastError(), ndev = 0;
+        for (int d = 0; d < ndev; ++d) {
+            const PoolStats p = pool_stats(d);
+            if (p.cached_blocks == 0 && p.live_blocks == 0) continue;
+            std::snprintf(line, sizeof line, "workspace pool, device %d : %g GiB cached in %zu blocks, %g GiB in use in %zu blocks\n",
+                          d, p.cached_bytes / 1073741824.0, p.cached_blocks, p.live_bytes / 1073741824.0,
+                          p.live_blocks);
+            s += line;
+        }
+        return s;
+    }
+
+    void live_allocations(long long *blocks, long long *bytes) {
+        *blocks = *bytes = 0;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess) cudaGetLastError(), ndev = 0;
+        for (int d = 0; d < ndev; ++d) {
+            const PoolStats p = pool_stats(d);
+            *blocks += (long long)p.live_blocks, *bytes += (long long)p.live_bytes;
+        }
+    }
+
+    std::string allocations_report() {
+        long long blocks = 0, bytes = 0;
+        live_allocations(&blocks, &bytes);
+        if (blocks == 0) return std::string();
+        std::string s = "Current memory allocation from superbblas:\n-----------------------------\n";
+        char line[256];
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess) cudaGetLastError(), ndev = 0;
+        for (int d = 0; d < ndev; ++d) {
+            const PoolStats p = pool_stats(d);
+            if (p.live_blocks == 0) continue;
+            std::snprintf(line, sizeof line, "device %d: %zu blocks, %g GiB\n", d, p.live_blocks,
+                          p.live_bytes / 1073741824.0);
+            s += line;
+        }
+        return s;
     }
 }
 
@@ -186,6 +371,36 @@ int sbb_profile_enable(int on) { SBB_TRY(profile_enable(on != 0)); }
 int sbb_profile_read(const char *kernel, double *total_ms, long long *count) {
     SBB_TRY(profile_read(kernel, total_ms, count));
 }
+
+int sbb_track_time(int on) { SBB_TRY(g_track_time = on != 0); }
+
+int sbb_reset_timings(void) {
+    SBB_TRY({
+        resolve_intervals();
+        g_timings.clear();
+    });
+}
+
+int sbb_report(int what, char *buf, size_t buflen, size_t *needed) {
+    try {
+        const std::string s = what == 0   ? timings_report()
+                              : what == 1 ? cache_report()
+                              : what == 2 ? allocations_report()
+                                          : throw std::runtime_error("sbb_report: unknown report");
+        if (needed) *needed = s.size() + 1;
+        if (s.size() + 1 > buflen) {
+            g_error = "buffer too small";
+            return 2;
+        }
+        std::memcpy(buf, s.c_str(), s.size() + 1);
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return 1;
+    }
+}
+
+int sbb_live_allocations(long long *blocks, long long *bytes) { SBB_TRY(live_allocations(blocks, bytes)); }
 
 int sbb_comm_unique_id(void *id128) { SBB_TRY(nccl_unique_id(id128)); }
 
@@ -323,6 +538,9 @@ int sbb_copy(int dtype0, int dtype1, const double *alpha, int nd0, const int *p0
              void *const *v1, const float *const *mask1, const sbb_context *ctx1, sbb_comm_t comm,
              int co, int copyadd) {
     SBB_TRY({
+        Tracker tracker("copy", [&] {
+            return tracked_device((Comm *)comm, {{ctx1, ncomponents1}, {ctx0, ncomponents0}});
+        });
         auto e = make_copy(dtype0, dtype1, alpha, nd0, p0, ncomponents0, o0, from0, size0, dim0, v0, mask0,
                            ctx0, nd1, p1, ncomponents1, o1, from1, dim1, v1, mask1, ctx1, (Comm *)comm, co,
                            copyadd);
@@ -340,6 +558,9 @@ int sbb_copy_begin(int dtype0, int dtype1, const double *alpha, int nd0, const i
                    sbb_request_t *request) {
     SBB_TRY({
         *request = nullptr;
+        Tracker tracker("copy_begin", [&] {
+            return tracked_device((Comm *)comm, {{ctx1, ncomponents1}, {ctx0, ncomponents0}});
+        });
         auto e = make_copy(dtype0, dtype1, alpha, nd0, p0, ncomponents0, o0, from0, size0, dim0, v0, mask0,
                            ctx0, nd1, p1, ncomponents1, o1, from1, dim1, v1, mask1, ctx1, (Comm *)comm, co,
                            copyadd);
@@ -351,7 +572,10 @@ int sbb_copy_begin(int dtype0, int dtype1, const double *alpha, int nd0, const i
 int sbb_request_wait(sbb_request_t request) {
     if (!request) return 0;
     std::unique_ptr<CopyExec> e((CopyExec *)request); // released whether or not the completion works
-    SBB_TRY(e->finish());
+    SBB_TRY({
+        Tracker tracker("wait", [] { return -1; }); // host time, bytes of the unpack kernels
+        e->finish();
+    });
 }
 
 int sbb_copy_plan_describe(int elem_size1, int nd0, const int *p0, int ncomponents0, const char *o0,
@@ -389,6 +613,9 @@ int sbb_contraction(int dtype, const double *alpha, int nd0, const int *p0, cons
                     const sbb_context *ctxr, sbb_comm_t comm, int co) {
     SBB_TRY({
         Comm *c = (Comm *)comm;
+        Tracker tracker("contraction", [&] {
+            return tracked_device(c, {{ctxr, ncomponentsr}, {ctx0, ncomponents0}, {ctx1, ncomponents1}});
+        });
         const int nranks = c ? c->nranks : 1, rank = c ? c->rank : 0;
         if (co != SBB_SLOW_TO_FAST && co != SBB_FAST_TO_SLOW)
             throw std::runtime_error("invalid coordinate order");

@@ -444,6 +444,16 @@ namespace sbb {
             use_device(dev);
             contract(d, a.dtype, a.alpha, big0 ? bptr : sptr, big0 ? sptr : bptr,
                      direct ? a.beta : zero, ov.ptr + ov.off * es, dev, device_state(dev).stream);
+            {
+                double vt = 1, vm = 1, vn = 1, vk = 1;
+                for (int i = 0; i < d.nT; ++i) vt *= d.T[i].size;
+                for (int i = 0; i < d.nM; ++i) vm *= d.M[i].size;
+                for (int i = 0; i < d.nN; ++i) vn *= d.N[i].size;
+                for (int i = 0; i < d.nK; ++i) vk *= d.K[i].size;
+                const bool cplx = a.dtype == SBB_C64 || a.dtype == SBB_C128;
+                work_counters().flops += (cplx ? 8.0 : 2.0) * vt * vm * vn * vk;
+                work_counters().bytes += vt * (vm * vk + vn * vk + vm * vn) * (double)es;
+            }
         }
 
         order_streams(devs);

@@ -421,4 +421,9 @@ namespace sbb {
         cache().clear();
     }
 
+    size_t plan_cache_size() {
+        std::lock_guard<std::mutex> g(cache_mutex);
+        return cache().size();
+    }
+
 } // namespace sbb

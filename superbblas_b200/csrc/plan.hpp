@@ -78,5 +78,7 @@ namespace sbb {
     /// Cached version (key = every field of CopyArgs)
     std::shared_ptr<const CopyPlan> get_copy_plan(const CopyArgs &a);
     void clear_plan_cache();
+    /// Plans held by the cache
+    size_t plan_cache_size();
 
 } // namespace sbb

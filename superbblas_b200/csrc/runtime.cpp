@@ -187,6 +187,20 @@ namespace sbb {
         p.live.erase(it);
     }
 
+    PoolStats pool_stats(int device) {
+        PoolStats r;
+        if (device < 0 || device >= MAX_DEVICES) return r;
+        const Pool &p = g_pool[device];
+        for (const auto &b : p.live) r.live_bytes += b.second, ++r.live_blocks;
+        for (const auto &b : p.free_blocks) r.cached_bytes += b.first, ++r.cached_blocks;
+        return r;
+    }
+
+    WorkCounters &work_counters() {
+        static WorkCounters w;
+        return w;
+    }
+
     void pool_clear() {
         for (int d = 0; d < MAX_DEVICES; ++d) {
             Pool &p = g_pool[d];
@@ -684,6 +698,13 @@ namespace sbb {
             } guard(use_aux && aux_grid > 0 && op.kind != BoxOp::Pack, aux_grid);
             const double one[2] = {1, 0}, zero[2] = {0, 0};
             sbk_box_desc desc = to_desc(op);
+            {
+                // the reference's `memops`: every moved element counts sizeof(T) + sizeof(Q) once,
+                // wherever its two ends are (the hop through an arena or a send buffer does not count)
+                const int from = op.kind == BoxOp::Local || op.kind == BoxOp::Pack ? es0 : 0;
+                const int to = op.kind == BoxOp::Pack ? 0 : es1;
+                work_counters().bytes += (double)op.volume() * (double)(from + to);
+            }
             switch (op.kind) {
             case BoxOp::Local: {
                 const Resolved &a = s[op.src_comp], &b = d[op.dst_comp];

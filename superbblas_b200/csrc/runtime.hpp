@@ -31,6 +31,20 @@ namespace sbb {
     void *pool_alloc(int device, size_t bytes);
     void pool_free(int device, void *p);
     void pool_clear();
+    /// Bytes / blocks handed out and not returned, and cached for reuse, on one device
+    struct PoolStats {
+        size_t live_bytes = 0, live_blocks = 0, cached_bytes = 0, cached_blocks = 0;
+    };
+    PoolStats pool_stats(int device);
+
+    /// Work queued by the executors so far, in the reference's units (tensor.h:1087-1088, :1593):
+    /// bytes = elements moved x (sizeof source + sizeof destination element) per copy kernel,
+    /// flops = 8 (complex) or 2 (real) x T.M.N.K per contraction kernel.  Read by the SB_TRACK_TIME
+    /// report of the public calls (capi.cpp); plain process-wide counters, like every other state here.
+    struct WorkCounters {
+        double flops = 0, bytes = 0;
+    };
+    WorkCounters &work_counters();
 
     class CopyExec;
     struct Comm;

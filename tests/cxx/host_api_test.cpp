@@ -7,6 +7,8 @@
 #include <cstdlib>
 #include <random>
 #include <set>
+#include <sstream>
+#include <string>
 
 using namespace superbblas;
 using namespace superbblas::detail;
@@ -137,6 +139,24 @@ int main() {
                     CHECK(z[i + 2 * k] == acc);
                 }
         }
+    }
+    // reports of the reference (performance.h:357-518): silent unless SB_TRACK_TIME / SB_TRACK_MEMORY
+    // are set; with them, the calls above appear by name and nothing of the allocator is left behind
+    {
+        std::ostringstream os;
+        reportTimings(os);
+        reportCacheUsage(os);
+        checkForMemoryLeaks(os);
+        const char *tt = std::getenv("SB_TRACK_TIME"), *tm = std::getenv("SB_TRACK_MEMORY");
+        const bool time_on = tt && std::atoi(tt) != 0, mem_on = tm && std::atoi(tm) != 0;
+        const std::string text = os.str();
+        CHECK((text.find("copy : ") != std::string::npos) == time_on);
+        CHECK((text.find("Cache usage") != std::string::npos) == mem_on);
+        resetTimings();
+        std::ostringstream os2;
+        reportTimings(os2);
+        CHECK(os2.str().find("copy : ") == std::string::npos);
+        std::printf("%s", text.c_str());
     }
     std::printf("host api ok\n");
     return 0;

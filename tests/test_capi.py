@@ -110,6 +110,51 @@ def test_cxx_front_end_host_checks(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "host api ok" in r.stdout, r.stdout + r.stderr
+    assert "Timing of superbblas kernels" not in r.stdout
+    # the reference's reports, switched on the reference's way
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, SB_TRACK_TIME="1", SB_TRACK_MEMORY="1"))
+    assert r.returncode == 0 and "host api ok" in r.stdout, r.stdout + r.stderr
+    assert "Timing of superbblas kernels" in r.stdout and "copy : " in r.stdout
+
+
+def test_reports_of_the_public_calls():
+    """sbb_report / sbb_track_time (performance.h:357-518): names, counts and text format; the
+    numbers themselves need a GPU (tests/test_gpu_report.py)."""
+    sb.trackTime(False)
+    sb.resetTimings()
+    assert sb.reportTimings() == ""
+    sb.trackTime(True)
+    try:
+        p = np.array([[[0, 0], [4, 4]]], dtype=np.int32)
+        x, y = np.zeros(16), np.zeros(16)
+        cpu = sb.createCpuContext()
+        for _ in range(3):
+            try:
+                sb.copy(1, p, 1, "ab", [0, 0], [4, 4], [4, 4], [x], None, cpu, p, 1, "ba", [0, 0], [4, 4],
+                        [y], None, cpu, sb.FastToSlow, sb.Copy)
+            except RuntimeError:
+                assert sb.getGpuDevicesCount() == 0   # fails only without a device; counted all the same
+        t = sb.timings()
+        assert set(t) == {"copy"} and t["copy"]["calls"] == 3
+        if sb.getGpuDevicesCount() > 0:
+            assert t["copy"]["bytes"] == 3 * 16 * (8 + 8)
+        lines = sb.reportTimings().splitlines()
+        assert lines[0] == "Timing of superbblas kernels:" and lines[2].startswith("copy : ")
+        for word in ("gpu_time:", "calls:", "flops:", "bytes:", "GFLOPs_single:", "GBYTES/s:", "intensity:"):
+            assert word in lines[2]
+        # a buffer that is too small is reported with the size needed
+        lib = ctypes.CDLL(sb.LIB_PATH)
+        small = ctypes.create_string_buffer(8)
+        needed = ctypes.c_size_t(0)
+        assert lib.sbb_report(0, small, ctypes.c_size_t(8), ctypes.byref(needed)) == 2
+        assert needed.value == len(sb.reportTimings()) + 1
+        assert lib.sbb_report(7, small, ctypes.c_size_t(8), ctypes.byref(needed)) == 1
+        assert "copy plans" in sb.reportCacheUsage()
+        sb.resetTimings()
+        assert sb.timings() == {}
+    finally:
+        sb.trackTime(False)
 
 
 @pytest.mark.parametrize("program", ["dist.cpp", "contract.cpp"])
