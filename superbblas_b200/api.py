@@ -522,6 +522,35 @@ def permute_copy(desc, src, dst, alpha=1, add=False, device=0):
                                  dtd, _scalar(alpha), int(add), device, None))
 
 
+class ContractDim(ctypes.Structure):
+    _fields_ = [("size", ctypes.c_int), ("s0", ctypes.c_int64), ("s1", ctypes.c_int64),
+                ("sr", ctypes.c_int64)]
+
+
+class ContractDesc(ctypes.Structure):
+    _fields_ = [("nT", ctypes.c_int), ("nM", ctypes.c_int), ("nN", ctypes.c_int), ("nK", ctypes.c_int),
+                ("T", ContractDim * 8), ("M", ContractDim * 8), ("N", ContractDim * 8),
+                ("K", ContractDim * 8), ("conj0", ctypes.c_int), ("conj1", ctypes.c_int)]
+
+
+def contract_desc(T=(), M=(), N=(), K=(), conj0=False, conj1=False):
+    """sbk_contract_desc from lists of (size, stride in v0, stride in v1, stride in vr) per label."""
+    d = ContractDesc()
+    for name, dims in (("T", T), ("M", M), ("N", N), ("K", K)):
+        setattr(d, "n" + name, len(dims))
+        for i, (size, s0, s1, sr) in enumerate(dims):
+            getattr(d, name)[i] = ContractDim(int(size), int(s0), int(s1), int(sr))
+    d.conj0, d.conj1 = int(bool(conj0)), int(bool(conj1))
+    return d
+
+
+def contract_describe(desc, dtype):
+    """Which kernel `sbk_contract` would launch for this problem, and how (host only)."""
+    buf = ctypes.create_string_buffer(512)
+    check(lib().sbk_contract_describe(ctypes.byref(desc), int(dtype), buf, ctypes.c_size_t(512)))
+    return buf.value.decode()
+
+
 def permute_describe(desc, dtype_src, dtype_dst, alpha=1, add=False, src_ptr=0, dst_ptr=0):
     buf = ctypes.create_string_buffer(512)
     check(lib().sbk_permute_describe(ctypes.byref(desc), dtype_src, dtype_dst, _scalar(alpha),

@@ -73,6 +73,11 @@ namespace sbb {
     /// Drop the cached launches of permute_copy (and their device tables)
     void permute_cache_clear();
 
+    /// SMs of a device.  When only a description of a launch is asked for (`describe_only`) and there
+    /// is no usable device, the B200's 148 -- the one target of this library -- so that the dispatch
+    /// and the K split of the contraction kernels can be examined (and are tested) on any host.
+    int sm_count(int device, bool describe_only = false);
+
     /// vr = alpha * sum_K f0(v0) f1(v1) + beta * vr. The current device must be `device`.
     void contract(const sbk_contract_desc &desc, int dtype, const double *alpha, const void *v0,
                   const void *v1, const double *beta, void *vr, int device, cudaStream_t stream,

@@ -661,14 +661,6 @@ namespace sbb {
             return g;
         }
 
-        int sm_count(int device) {
-            static int sms[64] = {0};
-            if (!sms[device])
-                cuda_check(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device),
-                           "cudaDeviceGetAttribute");
-            return sms[device];
-        }
-
         template <typename T> T scalar_of(const double *a);
         template <> double scalar_of<double>(const double *a) { return a[0]; }
         template <> double2 scalar_of<double2>(const double *a) { return make_double2(a[0], a[1]); }
@@ -760,7 +752,7 @@ namespace sbb {
 
             // K split: fill the machine for several waves, keep every slice long
             const long long tiles = p.T.vol * p.mtiles * p.ntiles;
-            const long long slots = (long long)sm_count(device) * MINB;
+            const long long slots = (long long)sm_count(device, describe != nullptr) * MINB;
             int best = 1;
             double best_eff = -1;
             const int smax = std::max(1, p.ksteps / 32);
@@ -811,6 +803,22 @@ namespace sbb {
         }
 
     } // namespace
+
+    int sm_count(int device, bool describe_only) {
+        static int sms[64] = {0};
+        if (device < 0 || device >= 64) throw std::runtime_error("invalid device");
+        if (!sms[device]) {
+            int n = 0;
+            const cudaError_t e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+            if (e != cudaSuccess && describe_only) {
+                cudaGetLastError();
+                return 148; // B200; not remembered: a real launch must ask the device
+            }
+            cuda_check(e, "cudaDeviceGetAttribute");
+            sms[device] = n;
+        }
+        return sms[device];
+    }
 
     void contract(const sbk_contract_desc &desc, int dtype, const double *alpha, const void *v0,
                   const void *v1, const double *beta, void *vr, int device, cudaStream_t stream,
@@ -876,7 +884,7 @@ namespace sbb {
         const bool want_row = force ? std::strcmp(force, "row") == 0 : true;
         if (want_dot && (force || p.K.vol >= 1024) && dotk::eligible(desc)) {
             dotk::DotParams dp;
-            dotk::build(desc, dp, (long long)sm_count(device) * 2048);
+            dotk::build(desc, dp, (long long)sm_count(device, describe != nullptr) * 2048);
             // (bounds the workspace: 2 bytes per thread with the CTA tree, 256 without)
             if (dotk::threads_of(dp) <= (dotk::cta_tree(dp) ? (1ll << 26) : (1ll << 20))) {
                 if (describe) {

@@ -468,14 +468,6 @@ namespace sbb {
                 return m;
             }
 
-            int sm_count(int device) {
-                static int sms[64] = {0};
-                if (!sms[device])
-                    cuda_check(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device),
-                               "cudaDeviceGetAttribute");
-                return sms[device];
-            }
-
         } // namespace
 
         bool eligible(const Problem &p, const void *v0, const void *v1) {
@@ -510,7 +502,7 @@ namespace sbb {
             const long long tiles = tvol * p.mtiles * p.ntiles;
             // K split: one CTA per SM; fill the machine in whole waves, keep slices >= 8 stages and
             // the workspace small (fewest slices within 3 % of the best wave efficiency)
-            const long long slots = sm_count(device);
+            const long long slots = sm_count(device, describe != nullptr);
             const int smax = std::max(1, std::min(p.ksteps / 8, 4096));
             double best_eff = -1;
             for (int s = 1; s <= smax; ++s) {
