@@ -172,3 +172,33 @@ def test_reference_tests_compile_against_the_drop_in_header(program):
                            ["-I" + os.path.join(ROOT, "tests", "cxx", "mpi_stub"),
                             "-I" + os.path.join(ROOT, "include"), src], capture_output=True, text=True)
         assert r.returncode == 0, (defs, r.stderr[-2000:])
+
+
+def test_front_end_marshalling_of_coordinates():
+    """superbblas_b200.api builds the int arrays of the C ABI from whatever sequence the caller has
+    and remembers them by VALUE: an array modified in place between two calls is a new value."""
+    from superbblas_b200 import api
+    assert list(api._iv([1, 2, 3], 3)) == [1, 2, 3]
+    assert list(api._iv((np.int64(4), np.int32(5)))) == [4, 5]
+    assert list(api._iv(np.array([[1, 2], [3, 4]], dtype=np.int64))) == [1, 2, 3, 4]
+    assert list(api._iv([[1, 2], [3, 4]])) == [1, 2, 3, 4]
+    assert list(api._iv([np.array([1, 2]), np.array([3, 4])])) == [1, 2, 3, 4]
+    a = np.array([7, 8, 9], dtype=np.int32)
+    first = api._iv(a)
+    assert api._iv(a) is first                       # same value: same marshalled array
+    a[1] = 80
+    assert list(api._iv(a)) == [7, 80, 9] and list(first) == [7, 8, 9]
+    v = np.arange(24, dtype=np.int32).reshape(2, 3, 4)[:, :, ::2]   # non-contiguous view
+    assert list(api._iv(v)) == [int(x) for x in v.reshape(-1)]
+    with pytest.raises(RuntimeError, match="wrong length"):
+        api._iv([1, 2], 3)
+    with pytest.raises(RuntimeError, match="wtf"):
+        api._partition(np.zeros((2, 2, 3), dtype=np.int32), 3, 3)
+    # the same partition through copy_plan as nested lists, int64 and int32 arrays
+    dim = [4, 6]
+    p32 = sb.basic_partitioning("ab", dim, [2, 1], "a", 2, 1)
+    q32 = sb.basic_partitioning("ab", dim, [1, 2], "b", 2, 1)
+    plans = [sb.copy_plan(8, p, 1, "ab", [0, 0], dim, dim, q, 1, "ab", [0, 1], dim, 2, 0, sb.FastToSlow, sb.Copy)
+             for p, q in ((p32, q32), (p32.astype(np.int64), q32.astype(np.int64)), (p32.tolist(), q32.tolist()))]
+    assert len(plans[0][0]) > 0
+    assert plans[0] == plans[1] == plans[2]
